@@ -1,0 +1,987 @@
+// Query hot path: multi-probe candidate scan + exact distance + top-k, batched over all
+// queries.  Replaces the per-query Python loop of Indexer.query (nlsh/indexer.py:62-95):
+// the index_select gather (77-82) disappears because buckets are contiguous in x_sorted,
+// distance_func (84-87 -> nlsh/data.py:109, :201) and topk (90-91) are fused into the scan.
+// The same kernel in "dense" mode (every query against every row) is the brute-force kNN
+// of precompute.py:57-67.
+//
+// Work decomposition (bucket-major so a bucket tile fetched once serves every query that
+// probes it):
+//   plan_count / plan_scan / plan_scatter : (query, probe) pairs grouped by bucket
+//   item = (bucket, row chunk, group of <= kG queries of that bucket)
+//   scan kernel: persistent CTAs pull items from an atomic counter.  One producer warp
+//     streams the chunk's rows HBM -> shared memory with 1-D bulk-async copies (TMA,
+//     SASS UBLKCP) into a ring of stages guarded by full/empty mbarriers; four consumer
+//     warps (one row per thread, padded row stride => conflict-free 128-bit LDS, query
+//     values broadcast) accumulate the distances of the row to the item's queries and
+//     keep one register-resident sorted top-k list per (warp, query).
+//   merge kernel: one warp per query merges its partial lists -> ids/dists/n_candidates.
+// All top-k decisions use the (distance, id) lexicographic order, so the result does not
+// depend on item scheduling or on how many GPUs the database is sharded over.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kConsumerWarps = 4;
+constexpr int kTileRows = 32 * kConsumerWarps;  // rows per stage
+constexpr int kG = 8;                           // queries per item
+constexpr int kChunkFloats = 64;                // columns per stage (256 B per row copy)
+constexpr int kMaxChunksPerBucket = 64;
+constexpr int kCtasPerSm = 2;
+constexpr size_t kSmemBudget = 112 * 1024;  // per CTA, leaves room for 2 CTAs / SM
+
+struct ScanGeom {
+  int d;         // real columns
+  int d_pad;     // row stride of x_sorted (multiple of 4)
+  int dc;        // columns per stage chunk (multiple of 4)
+  int n_chunks;  // ceil(d_pad / dc)
+  int stride_f;  // smem row stride in floats: (stride_f / 4) is odd => conflict-free LDS.128
+  int stages;
+  size_t stage_floats;
+  size_t smem_bytes;
+};
+
+ScanGeom scan_geom(int d, bool async) {
+  ScanGeom g;
+  g.d = d;
+  g.d_pad = (d + 3) / 4 * 4;
+  g.dc = g.d_pad < kChunkFloats ? g.d_pad : kChunkFloats;
+  g.n_chunks = (g.d_pad + g.dc - 1) / g.dc;
+  g.stride_f = ((g.dc / 4) % 2 == 0) ? g.dc + 4 : g.dc;
+  g.stage_floats = (size_t)kTileRows * g.stride_f;
+  const size_t q_bytes = (size_t)kG * g.d_pad * sizeof(float);
+  const size_t fixed = q_bytes + 256;
+  g.stages = 1;
+  if (async) {
+    g.stages = 4;
+    while (g.stages > 2 && fixed + g.stages * g.stage_floats * sizeof(float) > kSmemBudget) --g.stages;
+  }
+  g.smem_bytes = fixed + g.stages * g.stage_floats * sizeof(float);
+  return g;
+}
+
+struct ScanPolicy {
+  int rchunk;      // rows per item chunk (multiple of kTileRows)
+  int max_chunks;  // chunks of the largest bucket
+};
+
+ScanPolicy scan_policy(int64_t n_queries, int p, int n_buckets, int64_t n_rows,
+                       int64_t max_bucket_rows) {
+  const int64_t grid = (int64_t)nlsh_num_sms() * kCtasPerSm;
+  const int64_t target_items = grid * 8;
+  const int64_t pairs = n_queries * p > 0 ? n_queries * p : 1;
+  const int64_t distinct = pairs < n_buckets ? pairs : n_buckets;
+  int64_t groups = pairs / kG;
+  if (groups < distinct) groups = distinct;
+  if (groups < 1) groups = 1;
+  const int64_t chunks_needed = (target_items + groups - 1) / groups;
+  int64_t avg_bucket = n_rows / (n_buckets > 0 ? n_buckets : 1);
+  if (avg_bucket < 1) avg_bucket = 1;
+  int64_t rchunk = (avg_bucket + chunks_needed - 1) / chunks_needed;
+  if (max_bucket_rows < 1) max_bucket_rows = 1;
+  const int64_t floor_rchunk = (max_bucket_rows + kMaxChunksPerBucket - 1) / kMaxChunksPerBucket;
+  if (rchunk < floor_rchunk) rchunk = floor_rchunk;
+  rchunk = (rchunk + kTileRows - 1) / kTileRows * kTileRows;
+  ScanPolicy pol;
+  pol.rchunk = (int)rchunk;
+  pol.max_chunks = (int)((max_bucket_rows + rchunk - 1) / rchunk);
+  if (pol.max_chunks < 1) pol.max_chunks = 1;
+  return pol;
+}
+
+struct ScanArgs {
+  const float* xs;    // [n_rows, d_pad]
+  const int* ids;     // [n_rows] (probe mode) or nullptr (dense: id = row)
+  const int* offsets;  // [n_buckets + 1] (probe mode)
+  const float* q;     // [n_queries, d] (pre-normalised for the cosine metrics)
+  const int* pair_off;
+  const int* pairs;
+  const int* item_off;
+  int* item_counter;
+  float* part_d;
+  int* part_id;
+  long long n_rows;
+  long long self_offset;
+  int n_queries;
+  int n_buckets;
+  int p;
+  int k;
+  int rchunk;
+  int max_chunks;
+  int dense;
+  int dense_qgroups;
+  int dense_items;
+  int exclude_self;
+  int d, d_pad, dc, n_chunks, stride_f, stages;
+};
+
+// ---- per-chunk distance accumulation ----------------------------------------------------
+// xrow: this thread's row inside the stage (stride-padded), qs: query values of this chunk
+// (query g at qs + g * d_pad), nvec full float4 columns, tail = extra valid columns (0..3).
+template <int METRIC, int NG>
+__device__ __forceinline__ void consume_chunk(float (&acc)[kG], float& xx,
+                                              const float* __restrict__ xrow,
+                                              const float* __restrict__ qs, int d_pad, int nvec,
+                                              int tail) {
+  const float4* x4 = reinterpret_cast<const float4*>(xrow);
+#pragma unroll 4
+  for (int v = 0; v < nvec; ++v) {
+    const float4 xv = x4[v];
+    if (METRIC == NLSH_METRIC_ANGULAR || METRIC == NLSH_METRIC_COSINE) {
+      xx = fmaf(xv.x, xv.x, xx);
+      xx = fmaf(xv.y, xv.y, xx);
+      xx = fmaf(xv.z, xv.z, xx);
+      xx = fmaf(xv.w, xv.w, xx);
+    }
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float4 qv = *reinterpret_cast<const float4*>(qs + g * d_pad + 4 * v);
+      if (METRIC == NLSH_METRIC_L2) {
+        // F.pairwise_distance: (q - x) + eps, squared and summed (nlsh/data.py:201)
+        float t;
+        t = __fadd_rn(__fsub_rn(qv.x, xv.x), 1e-6f); acc[g] = fmaf(t, t, acc[g]);
+        t = __fadd_rn(__fsub_rn(qv.y, xv.y), 1e-6f); acc[g] = fmaf(t, t, acc[g]);
+        t = __fadd_rn(__fsub_rn(qv.z, xv.z), 1e-6f); acc[g] = fmaf(t, t, acc[g]);
+        t = __fadd_rn(__fsub_rn(qv.w, xv.w), 1e-6f); acc[g] = fmaf(t, t, acc[g]);
+      } else if (METRIC == NLSH_METRIC_L2SQ) {
+        float t;
+        t = qv.x - xv.x; acc[g] = fmaf(t, t, acc[g]);
+        t = qv.y - xv.y; acc[g] = fmaf(t, t, acc[g]);
+        t = qv.z - xv.z; acc[g] = fmaf(t, t, acc[g]);
+        t = qv.w - xv.w; acc[g] = fmaf(t, t, acc[g]);
+      } else {
+        acc[g] = fmaf(qv.x, xv.x, acc[g]);
+        acc[g] = fmaf(qv.y, xv.y, acc[g]);
+        acc[g] = fmaf(qv.z, xv.z, acc[g]);
+        acc[g] = fmaf(qv.w, xv.w, acc[g]);
+      }
+    }
+  }
+  // partial last vector (d not a multiple of 4): only the first `tail` components exist
+  for (int c = 0; c < tail; ++c) {
+    const float xv = xrow[4 * nvec + c];
+    if (METRIC == NLSH_METRIC_ANGULAR || METRIC == NLSH_METRIC_COSINE) xx = fmaf(xv, xv, xx);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float qv = qs[g * d_pad + 4 * nvec + c];
+      if (METRIC == NLSH_METRIC_L2) {
+        const float t = __fadd_rn(__fsub_rn(qv, xv), 1e-6f);
+        acc[g] = fmaf(t, t, acc[g]);
+      } else if (METRIC == NLSH_METRIC_L2SQ) {
+        const float t = qv - xv;
+        acc[g] = fmaf(t, t, acc[g]);
+      } else {
+        acc[g] = fmaf(qv, xv, acc[g]);
+      }
+    }
+  }
+}
+
+template <int METRIC>
+__device__ __forceinline__ void consume_dispatch(int ng, float (&acc)[kG], float& xx,
+                                                 const float* xrow, const float* qs, int d_pad,
+                                                 int nvec, int tail) {
+  if (ng <= 1)
+    consume_chunk<METRIC, 1>(acc, xx, xrow, qs, d_pad, nvec, tail);
+  else if (ng <= 2)
+    consume_chunk<METRIC, 2>(acc, xx, xrow, qs, d_pad, nvec, tail);
+  else if (ng <= 4)
+    consume_chunk<METRIC, 4>(acc, xx, xrow, qs, d_pad, nvec, tail);
+  else
+    consume_chunk<METRIC, 8>(acc, xx, xrow, qs, d_pad, nvec, tail);
+}
+
+template <int METRIC>
+__device__ __forceinline__ float finalize_distance(float acc, float xx) {
+  if (METRIC == NLSH_METRIC_L2) return sqrtf(acc);
+  if (METRIC == NLSH_METRIC_L2SQ) return acc;
+  if (METRIC == NLSH_METRIC_ANGULAR) return 1.0f - acc / fmaxf(sqrtf(xx), 1e-8f);
+  return 1.0f - acc / sqrtf(xx);  // precompute._cosine_distance: no clamp
+}
+
+struct Item {
+  long long row0, row1;  // rows of x_sorted covered by this item
+  int ng;                // queries in this item (1..kG)
+  int chunk;             // chunk index inside the bucket / dense row block
+  int pair_base;         // probe mode: first entry of `pairs`; dense: first query index
+};
+
+__device__ __forceinline__ Item decode_item(const ScanArgs& a, int item) {
+  Item it;
+  if (a.dense) {
+    const int blk = item / a.dense_qgroups;
+    const int gq = item - blk * a.dense_qgroups;
+    it.row0 = (long long)blk * a.rchunk;
+    it.row1 = it.row0 + a.rchunk;
+    if (it.row1 > a.n_rows || blk == a.max_chunks - 1) it.row1 = a.n_rows;
+    it.chunk = blk;
+    it.pair_base = gq * kG;
+    const int left = a.n_queries - it.pair_base;
+    it.ng = left < kG ? left : kG;
+    return it;
+  }
+  // largest b with item_off[b] <= item
+  int lo = 0, hi = a.n_buckets;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (a.item_off[mid] <= item) lo = mid; else hi = mid;
+  }
+  const int b = lo;
+  const int local = item - a.item_off[b];
+  const int p0 = a.pair_off[b];
+  const int nq = a.pair_off[b + 1] - p0;
+  const int ngroups = (nq + kG - 1) / kG;
+  const int c = local / ngroups;
+  const int gq = local - c * ngroups;
+  const int r0 = a.offsets[b];
+  const int size = a.offsets[b + 1] - r0;
+  int nch = (size + a.rchunk - 1) / a.rchunk;
+  if (nch > a.max_chunks) nch = a.max_chunks;
+  it.row0 = (long long)r0 + (long long)c * a.rchunk;
+  it.row1 = (c == nch - 1) ? (long long)r0 + size : it.row0 + a.rchunk;
+  it.chunk = c;
+  it.pair_base = p0 + gq * kG;
+  const int left = nq - gq * kG;
+  it.ng = left < kG ? left : kG;
+  return it;
+}
+
+// Scan kernel.  ASYNC: warps 0..3 consume, warp 4 produces with bulk-async copies.
+// !ASYNC (debug / A-B): 4 warps stage each chunk cooperatively with plain loads.
+template <int METRIC, int KPL, bool ASYNC>
+__global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kConsumerWarps, kCtasPerSm)
+    scan_kernel(const ScanArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage_buf = reinterpret_cast<float*>(smem_raw);
+  float* qs = stage_buf + (size_t)a.stages * kTileRows * a.stride_f;
+  unsigned char* tail_ptr = reinterpret_cast<unsigned char*>(qs + (size_t)kG * a.d_pad);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail_ptr);  // [stages <= 4]
+  uint64_t* empty_bar = full_bar + 4;                          // [stages <= 4]
+  int* s_f = reinterpret_cast<int*>(empty_bar + 4);            // [kG] flat probe index / query
+  int* s_item = s_f + kG;                                      // [2]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const size_t stage_floats = (size_t)kTileRows * a.stride_f;
+
+  if (ASYNC && tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  const int total_items = a.dense ? a.dense_items : a.item_off[a.n_buckets];
+  if (tid == 0) s_item[0] = atomicAdd(a.item_counter, 1);
+  __syncthreads();
+
+  unsigned ring = 0;  // stage uses so far (same sequence in producer and consumers)
+  int round = 0;
+  int item = s_item[0];
+  const int tail_cols = a.d - (a.d_pad - 4);  // valid columns of the last float4 (1..4)
+
+  while (item < total_items) {
+    if (tid == 0) s_item[(round + 1) & 1] = atomicAdd(a.item_counter, 1);
+    const Item it = decode_item(a, item);
+    const int n_tiles = (int)((it.row1 - it.row0 + kTileRows - 1) / kTileRows);
+
+    if (warp < kConsumerWarps) {
+      // ---- stage the item's queries: qs[g][0..d_pad) -----------------------------------
+      const int ctid = tid;  // 0..127
+      if (ctid < kG) {
+        int f = -1;
+        if (ctid < it.ng) f = a.dense ? it.pair_base + ctid : a.pairs[it.pair_base + ctid];
+        s_f[ctid] = f;
+      }
+      for (int g = 0; g < kG; ++g) {
+        int qidx = -1;
+        if (g < it.ng) {
+          const int f = a.dense ? it.pair_base + g : a.pairs[it.pair_base + g];
+          qidx = a.dense ? f : f / a.p;
+        }
+        for (int c = ctid; c < a.d_pad; c += 32 * kConsumerWarps)
+          qs[g * a.d_pad + c] = (qidx >= 0 && c < a.d) ? a.q[(size_t)qidx * a.d + c] : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory");
+
+      WarpTopK<KPL, int> top[kG];
+#pragma unroll
+      for (int g = 0; g < kG; ++g) top[g].init(NLSH_ID_SENTINEL);
+      int self_id[kG];
+#pragma unroll
+      for (int g = 0; g < kG; ++g) self_id[g] = -1;
+      if (a.exclude_self) {
+#pragma unroll
+        for (int g = 0; g < kG; ++g)
+          if (g < it.ng) self_id[g] = (int)(a.self_offset + s_f[g]);
+      }
+
+      const float* xrow_base = stage_buf + (size_t)(warp * 32 + lane) * a.stride_f;
+      for (int t = 0; t < n_tiles; ++t) {
+        const long long row = it.row0 + (long long)t * kTileRows + warp * 32 + lane;
+        const bool valid = row < it.row1;
+        int cand_id = NLSH_ID_SENTINEL;
+        if (valid) cand_id = a.ids ? a.ids[row] : (int)row;  // latency hidden behind the chunk loop
+        float acc[kG];
+#pragma unroll
+        for (int g = 0; g < kG; ++g) acc[g] = 0.f;
+        float xx = 0.f;
+        const long long tile_row0 = it.row0 + (long long)t * kTileRows;
+        const int rows_in_tile =
+            (int)((it.row1 - tile_row0) < kTileRows ? (it.row1 - tile_row0) : kTileRows);
+        for (int ch = 0; ch < a.n_chunks; ++ch) {
+          const int col0 = ch * a.dc;
+          const int cols = (a.d_pad - col0) < a.dc ? (a.d_pad - col0) : a.dc;
+          int nvec = cols >> 2;
+          int tail = 0;
+          if (ch == a.n_chunks - 1 && tail_cols < 4) {
+            nvec -= 1;
+            tail = tail_cols;
+          }
+          const int s = ASYNC ? (int)(ring % (unsigned)a.stages) : 0;
+          if (ASYNC) {
+            mbar_wait(&full_bar[s], (ring / (unsigned)a.stages) & 1u);
+          } else {
+            const int cvec = cols >> 2;
+            for (int idx = tid; idx < rows_in_tile * cvec; idx += 32 * kConsumerWarps) {
+              const int r = idx / cvec, v = idx - r * cvec;
+              const float4 val = __ldcs(reinterpret_cast<const float4*>(
+                                            a.xs + (size_t)(tile_row0 + r) * a.d_pad + col0) + v);
+              *reinterpret_cast<float4*>(stage_buf + (size_t)r * a.stride_f + 4 * v) = val;
+            }
+            __syncthreads();
+          }
+          consume_dispatch<METRIC>(it.ng, acc, xx, xrow_base + s * stage_floats, qs + col0, a.d_pad,
+                                   nvec, tail);
+          if (ASYNC) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+          } else {
+            __syncthreads();
+          }
+          ++ring;
+        }
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {
+          if (g < it.ng) {
+            const float dist = finalize_distance<METRIC>(acc[g], xx);
+            top[g].offer(dist, cand_id, valid && cand_id != self_id[g], a.k);
+          }
+        }
+      }
+      // ---- partial lists: one per (query-probe, chunk, warp) ---------------------------
+#pragma unroll
+      for (int g = 0; g < kG; ++g) {
+        if (g < it.ng) {
+          const size_t slot =
+              ((size_t)s_f[g] * a.max_chunks + it.chunk) * kConsumerWarps + warp;
+#pragma unroll
+          for (int j = 0; j < KPL; ++j) {
+            const int pos = j * 32 + lane;
+            if (pos < a.k) {
+              a.part_d[slot * a.k + pos] = top[g].d[j];
+              a.part_id[slot * a.k + pos] = top[g].id[j];
+            }
+          }
+        }
+      }
+    } else if (ASYNC) {
+      // ---- producer warp: stream the item's rows, chunk by chunk ----------------------
+      for (int t = 0; t < n_tiles; ++t) {
+        const long long tile_row0 = it.row0 + (long long)t * kTileRows;
+        const int rows_in_tile =
+            (int)((it.row1 - tile_row0) < kTileRows ? (it.row1 - tile_row0) : kTileRows);
+        for (int ch = 0; ch < a.n_chunks; ++ch) {
+          const int col0 = ch * a.dc;
+          const int cols = (a.d_pad - col0) < a.dc ? (a.d_pad - col0) : a.dc;
+          const unsigned bytes = (unsigned)cols * 4u;
+          const int s = (int)(ring % (unsigned)a.stages);
+          mbar_wait(&empty_bar[s], ((ring / (unsigned)a.stages) & 1u) ^ 1u);
+          if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], bytes * (unsigned)rows_in_tile);
+          __syncwarp();
+          float* dst = stage_buf + s * stage_floats;
+          const float* src = a.xs + (size_t)tile_row0 * a.d_pad + col0;
+          for (int r = lane; r < rows_in_tile; r += 32)
+            bulk_g2s(dst + (size_t)r * a.stride_f, src + (size_t)r * a.d_pad, bytes, &full_bar[s]);
+          ++ring;
+        }
+      }
+    }
+    __syncthreads();
+    ++round;
+    item = s_item[round & 1];
+  }
+}
+
+// ---- plan kernels ------------------------------------------------------------------------
+__device__ __forceinline__ bool probe_valid(const int* __restrict__ probes, const int* offsets,
+                                            int n_buckets, int p, long long f, int& b_out) {
+  const int b = probes[f];
+  b_out = b;
+  if (b < 0 || b >= n_buckets) return false;
+  if (offsets[b + 1] - offsets[b] <= 0) return false;
+  const long long row_base = f - (f % p);
+  for (long long e = row_base; e < f; ++e)
+    if (probes[e] == b) return false;  // duplicate probe: the reference probes a set
+  return true;
+}
+
+__global__ void plan_count_kernel(const int* __restrict__ probes, const int* __restrict__ offsets,
+                                  int n_buckets, int p, long long n_pairs, int* __restrict__ cnt) {
+  const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_pairs) return;
+  int b;
+  if (probe_valid(probes, offsets, n_buckets, p, f, b)) atomicAdd(&cnt[b], 1);
+}
+
+// One block: pair_off = exclusive scan of cnt, item_off = exclusive scan of items per bucket.
+__global__ void __launch_bounds__(1024)
+    plan_scan_kernel(const int* __restrict__ cnt, const int* __restrict__ offsets, int n_buckets,
+                     int rchunk, int max_chunks, int* __restrict__ pair_off,
+                     int* __restrict__ item_off) {
+  __shared__ int sw[2][33];
+  int carry_p = 0, carry_i = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n_buckets; base += blockDim.x) {
+    const int b = base + threadIdx.x;
+    int c = 0, items = 0;
+    if (b < n_buckets) {
+      c = cnt[b];
+      const int size = offsets[b + 1] - offsets[b];
+      int nch = (size + rchunk - 1) / rchunk;
+      if (nch > max_chunks) nch = max_chunks;
+      items = ((c + kG - 1) / kG) * nch;
+    }
+    int ic = c, ii = items;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tc = __shfl_up_sync(NLSH_FULL_MASK, ic, o);
+      const int ti = __shfl_up_sync(NLSH_FULL_MASK, ii, o);
+      if (lane >= o) {
+        ic += tc;
+        ii += ti;
+      }
+    }
+    if (lane == 31) {
+      sw[0][warp] = ic;
+      sw[1][warp] = ii;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int wc = sw[0][lane], wi = sw[1][lane];
+      int sc = wc, si = wi;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tc = __shfl_up_sync(NLSH_FULL_MASK, sc, o);
+        const int ti = __shfl_up_sync(NLSH_FULL_MASK, si, o);
+        if (lane >= o) {
+          sc += tc;
+          si += ti;
+        }
+      }
+      sw[0][lane] = sc - wc;
+      sw[1][lane] = si - wi;
+      if (lane == 31) {
+        sw[0][32] = sc;
+        sw[1][32] = si;
+      }
+    }
+    __syncthreads();
+    if (b < n_buckets) {
+      pair_off[b] = carry_p + sw[0][warp] + ic - c;
+      item_off[b] = carry_i + sw[1][warp] + ii - items;
+    }
+    carry_p += sw[0][32];
+    carry_i += sw[1][32];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    pair_off[n_buckets] = carry_p;
+    item_off[n_buckets] = carry_i;
+  }
+}
+
+__global__ void plan_scatter_kernel(const int* __restrict__ probes, const int* __restrict__ offsets,
+                                    int n_buckets, int p, long long n_pairs,
+                                    const int* __restrict__ pair_off, int* __restrict__ cursor,
+                                    int* __restrict__ pairs) {
+  const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_pairs) return;
+  int b;
+  if (probe_valid(probes, offsets, n_buckets, p, f, b))
+    pairs[pair_off[b] + atomicAdd(&cursor[b], 1)] = (int)f;
+}
+
+// q / max(|q|, eps) per row (eps = 0: plain normalisation as precompute._cosine_distance).
+__global__ void __launch_bounds__(128)
+    normalize_rows_kernel(const float* __restrict__ q, long long n, int d, float eps,
+                          float* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = lane_id();
+  float ss = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float v = q[row * d + c];
+    ss = fmaf(v, v, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(NLSH_FULL_MASK, ss, o);
+  float nrm = sqrtf(ss);
+  if (eps > 0.f) nrm = fmaxf(nrm, eps);
+  for (int c = lane; c < d; c += 32) out[row * d + c] = q[row * d + c] / nrm;
+}
+
+// One warp per query: merge the partial lists of its probes (or of the dense row blocks).
+template <int KPL>
+__global__ void __launch_bounds__(128)
+    merge_partials_kernel(const float* __restrict__ part_d, const int* __restrict__ part_id,
+                          const int* __restrict__ probes, const int* __restrict__ offsets,
+                          int n_buckets, int p, int k, int rchunk, int max_chunks, int dense,
+                          long long n_queries, long long id_offset, long long* __restrict__ ids_out,
+                          float* __restrict__ dists_out, int* __restrict__ ncand_out) {
+  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n_queries) return;
+  const int lane = lane_id();
+  WarpTopK<KPL, int> top;
+  top.init(NLSH_ID_SENTINEL);
+  int ncand = 0;
+  const int n_outer = dense ? 1 : p;
+  for (int j = 0; j < n_outer; ++j) {
+    long long f;
+    int nch;
+    if (dense) {
+      f = q;
+      nch = max_chunks;
+    } else {
+      f = q * p + j;
+      int b;
+      if (!probe_valid(probes, offsets, n_buckets, p, f, b)) continue;
+      const int size = offsets[b + 1] - offsets[b];
+      ncand += size;
+      nch = (size + rchunk - 1) / rchunk;
+      if (nch > max_chunks) nch = max_chunks;
+    }
+    for (int c = 0; c < nch; ++c) {
+      for (int w = 0; w < kConsumerWarps; ++w) {
+        const size_t base = (((size_t)f * max_chunks + c) * kConsumerWarps + w) * k;
+        for (int e0 = 0; e0 < k; e0 += 32) {
+          const int e = e0 + lane;
+          float cd = 0.f;
+          int cid = NLSH_ID_SENTINEL;
+          if (e < k) {
+            cd = part_d[base + e];
+            cid = part_id[base + e];
+          }
+          top.offer(cd, cid, cid != NLSH_ID_SENTINEL, k);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    const int pos = j * 32 + lane;
+    if (pos < k) {
+      const int id = top.id[j];
+      ids_out[q * k + pos] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
+      dists_out[q * k + pos] = top.d[j];
+    }
+  }
+  if (lane == 0 && ncand_out) ncand_out[q] = ncand;
+}
+
+// Cross-shard merge (after the NCCL all-gather): lists [n_lists, n_queries, k].
+template <int KPL>
+__global__ void __launch_bounds__(128)
+    merge_lists_kernel(const float* __restrict__ dists, const long long* __restrict__ ids,
+                       int n_lists, long long n_queries, int k, long long* __restrict__ ids_out,
+                       float* __restrict__ dists_out) {
+  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n_queries) return;
+  const int lane = lane_id();
+  const long long sentinel = 0x7fffffffffffffffll;
+  WarpTopK<KPL, long long> top;
+  top.init(sentinel);
+  for (int l = 0; l < n_lists; ++l) {
+    const size_t base = ((size_t)l * n_queries + q) * k;
+    for (int e0 = 0; e0 < k; e0 += 32) {
+      const int e = e0 + lane;
+      float cd = 0.f;
+      long long cid = -1;
+      if (e < k) {
+        cd = dists[base + e];
+        cid = ids[base + e];
+      }
+      top.offer(cd, cid, cid >= 0, k);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    const int pos = j * 32 + lane;
+    if (pos < k) {
+      const long long id = top.id[j];
+      ids_out[q * k + pos] = (id == sentinel) ? -1ll : id;
+      dists_out[q * k + pos] = top.d[j];
+    }
+  }
+}
+
+__global__ void fill_int_kernel(int* __restrict__ p, size_t n, int v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void recall_hits_kernel(const long long* __restrict__ gt, int k_gt,
+                                   const long long* __restrict__ pred, int k_pred,
+                                   long long n_queries, int* __restrict__ hits) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_queries) return;
+  // |set(gt) & set(pred)| (nlsh/metrics.py:4-7): count distinct gt ids present in pred
+  int h = 0;
+  for (int i = 0; i < k_gt; ++i) {
+    const long long g = gt[q * k_gt + i];
+    bool dup = false;
+    for (int i2 = 0; i2 < i; ++i2) dup |= (gt[q * k_gt + i2] == g);
+    if (dup) continue;
+    bool found = false;
+    for (int j = 0; j < k_pred; ++j) found |= (pred[q * k_pred + j] == g);
+    h += found ? 1 : 0;
+  }
+  hits[q] = h;
+}
+
+// ---- launch helpers ------------------------------------------------------------------------
+template <int METRIC, int KPL>
+int launch_scan(const ScanArgs& a, const ScanGeom& g, bool async, int grid, cudaStream_t st) {
+  if (async) {
+    auto kern = scan_kernel<METRIC, KPL, true>;
+    NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)g.smem_bytes));
+    kern<<<grid, 32 * (kConsumerWarps + 1), g.smem_bytes, st>>>(a);
+  } else {
+    auto kern = scan_kernel<METRIC, KPL, false>;
+    NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)g.smem_bytes));
+    kern<<<grid, 32 * kConsumerWarps, g.smem_bytes, st>>>(a);
+  }
+  return nlsh_check_cuda(cudaGetLastError(), "scan_kernel launch");
+}
+
+template <int METRIC>
+int launch_scan_k(const ScanArgs& a, const ScanGeom& g, bool async, int grid, cudaStream_t st) {
+  if (a.k <= 32) return launch_scan<METRIC, 1>(a, g, async, grid, st);
+  if (a.k <= 64) return launch_scan<METRIC, 2>(a, g, async, grid, st);
+  return launch_scan<METRIC, 4>(a, g, async, grid, st);
+}
+
+int launch_scan_metric(int metric, const ScanArgs& a, const ScanGeom& g, bool async, int grid,
+                       cudaStream_t st) {
+  switch (metric) {
+    case NLSH_METRIC_L2: return launch_scan_k<NLSH_METRIC_L2>(a, g, async, grid, st);
+    case NLSH_METRIC_ANGULAR: return launch_scan_k<NLSH_METRIC_ANGULAR>(a, g, async, grid, st);
+    case NLSH_METRIC_L2SQ: return launch_scan_k<NLSH_METRIC_L2SQ>(a, g, async, grid, st);
+    default: return launch_scan_k<NLSH_METRIC_COSINE>(a, g, async, grid, st);
+  }
+}
+
+int launch_merge_partials(const float* part_d, const int* part_id, const int* probes,
+                          const int* offsets, int n_buckets, int p, int k, int rchunk,
+                          int max_chunks, int dense, int64_t n_queries, int64_t id_offset,
+                          int64_t* ids_out, float* dists_out, int* ncand_out, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((n_queries + 3) / 4);
+  long long* ids_ll = reinterpret_cast<long long*>(ids_out);
+  if (k <= 32)
+    merge_partials_kernel<1><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
+                                                     k, rchunk, max_chunks, dense, n_queries,
+                                                     id_offset, ids_ll, dists_out, ncand_out);
+  else if (k <= 64)
+    merge_partials_kernel<2><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
+                                                     k, rchunk, max_chunks, dense, n_queries,
+                                                     id_offset, ids_ll, dists_out, ncand_out);
+  else
+    merge_partials_kernel<4><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
+                                                     k, rchunk, max_chunks, dense, n_queries,
+                                                     id_offset, ids_ll, dists_out, ncand_out);
+  return nlsh_check_cuda(cudaGetLastError(), "merge_partials_kernel launch");
+}
+
+struct QueryWorkspace {
+  int* cnt;       // [B]   (cnt, cursor, counter are zeroed with one memset)
+  int* cursor;    // [B]
+  int* counter;   // [1]
+  int* pair_off;  // [B+1]
+  int* item_off;  // [B+1]
+  int* pairs;     // [Q*p]
+  float* qn;      // [Q*d]
+  float* part_d;
+  int* part_id;
+  size_t zero_ints;
+  size_t total;
+};
+
+QueryWorkspace carve_query_ws(void* base, int64_t nq, int p, int k, int d, int n_buckets,
+                              int max_chunks) {
+  QueryWorkspace w;
+  WorkspaceCarver ws(base);
+  w.zero_ints = (size_t)2 * n_buckets + 64;
+  int* z = ws.take<int>(w.zero_ints);
+  w.cnt = z;
+  w.cursor = z ? z + n_buckets : nullptr;
+  w.counter = z ? z + 2 * n_buckets : nullptr;
+  w.pair_off = ws.take<int>((size_t)n_buckets + 1);
+  w.item_off = ws.take<int>((size_t)n_buckets + 1);
+  w.pairs = ws.take<int>((size_t)nq * p);
+  w.qn = ws.take<float>((size_t)nq * d);
+  const size_t lists = (size_t)nq * p * max_chunks * kConsumerWarps * k;
+  w.part_d = ws.take<float>(lists);
+  w.part_id = ws.take<int>(lists);
+  w.total = ws.total();
+  return w;
+}
+
+struct KnnPlan {
+  int n_blocks;
+  int rchunk;
+  int qgroups;
+};
+
+KnnPlan knn_plan(int64_t n_queries, int64_t n_rows) {
+  KnnPlan kp;
+  kp.qgroups = (int)((n_queries + kG - 1) / kG);
+  if (kp.qgroups < 1) kp.qgroups = 1;
+  const int64_t grid = (int64_t)nlsh_num_sms() * kCtasPerSm;
+  int64_t blocks = (grid * 8 + kp.qgroups - 1) / kp.qgroups;
+  const int64_t max_blocks = (n_rows + kTileRows - 1) / kTileRows;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks > 256) blocks = 256;
+  if (blocks < 1) blocks = 1;
+  int64_t rchunk = (n_rows + blocks - 1) / blocks;
+  rchunk = (rchunk + kTileRows - 1) / kTileRows * kTileRows;
+  if (rchunk < kTileRows) rchunk = kTileRows;
+  kp.rchunk = (int)rchunk;
+  kp.n_blocks = (int)((n_rows + rchunk - 1) / rchunk);
+  if (kp.n_blocks < 1) kp.n_blocks = 1;
+  return kp;
+}
+
+}  // namespace
+
+extern "C" size_t nlsh_query_workspace_bytes(int64_t n_queries, int32_t p, int32_t k, int32_t d,
+                                             int32_t n_buckets, int64_t n_rows,
+                                             int64_t max_bucket_rows) {
+  if (n_queries < 0 || p < 1 || k < 1 || d < 1 || n_buckets < 1) return 0;
+  const ScanPolicy pol = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows);
+  return carve_query_ws(nullptr, n_queries, p, k, d, n_buckets, pol.max_chunks).total;
+}
+
+extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t d,
+                                    const int32_t* probes, int32_t p, const int32_t* offsets,
+                                    int32_t n_buckets, const int32_t* ids, const float* x_sorted,
+                                    int64_t n_rows, int64_t max_bucket_rows, int32_t metric,
+                                    int32_t k, int64_t id_offset, int64_t* ids_out,
+                                    float* dists_out, int32_t* ncand_out, void* workspace,
+                                    size_t workspace_bytes, uint32_t flags, void* stream) {
+  NLSH_REQUIRE(n_queries >= 0 && n_queries * (int64_t)p < (1ll << 31),
+               "query: n_queries=%lld x p=%d outside [0, 2^31)", (long long)n_queries, p);
+  NLSH_REQUIRE(d >= 1 && d <= 16384, "query: d=%d outside [1, 16384]", d);
+  NLSH_REQUIRE(p >= 1 && p <= 1024, "query: p=%d outside [1, 1024]", p);
+  NLSH_REQUIRE(k >= 1 && k <= NLSH_MAX_K, "query: k=%d outside [1, %d]", k, NLSH_MAX_K);
+  NLSH_REQUIRE(n_buckets >= 1 && n_buckets <= (1 << 20), "query: n_buckets=%d outside [1, 2^20]",
+               n_buckets);
+  NLSH_REQUIRE(metric == NLSH_METRIC_L2 || metric == NLSH_METRIC_ANGULAR,
+               "query: metric %d is not a scan metric (L2=0 / ANGULAR=1)", metric);
+  NLSH_REQUIRE(n_rows >= 0 && n_rows < (1ll << 31), "query: n_rows=%lld outside [0, 2^31)",
+               (long long)n_rows);
+  if (n_queries == 0) return NLSH_OK;
+  NLSH_REQUIRE(xq && probes && offsets && ids_out && dists_out, "query: null pointer");
+  NLSH_REQUIRE(n_rows == 0 || (ids && x_sorted), "query: null index arrays");
+  NLSH_REQUIRE((reinterpret_cast<uintptr_t>(x_sorted) & 15) == 0, "query: x_sorted not 16-byte aligned");
+
+  const ScanPolicy pol = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows);
+  const QueryWorkspace w = carve_query_ws(workspace, n_queries, p, k, d, n_buckets, pol.max_chunks);
+  if (workspace == nullptr || workspace_bytes < w.total) {
+    nlsh_set_error("query: workspace %zu bytes < required %zu", workspace_bytes, w.total);
+    return NLSH_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool async = (flags & 1u) == 0;
+  const ScanGeom geom = scan_geom(d, async);
+  const long long n_pairs = (long long)n_queries * p;
+
+  NLSH_CUDA_TRY(cudaMemsetAsync(w.cnt, 0, w.zero_ints * sizeof(int), st));
+  plan_count_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(probes, offsets, n_buckets, p,
+                                                                     n_pairs, w.cnt);
+  NLSH_CUDA_TRY(cudaGetLastError());
+  plan_scan_kernel<<<1, 1024, 0, st>>>(w.cnt, offsets, n_buckets, pol.rchunk, pol.max_chunks,
+                                       w.pair_off, w.item_off);
+  NLSH_CUDA_TRY(cudaGetLastError());
+  plan_scatter_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(
+      probes, offsets, n_buckets, p, n_pairs, w.pair_off, w.cursor, w.pairs);
+  NLSH_CUDA_TRY(cudaGetLastError());
+
+  const float* q_used = xq;
+  if (metric == NLSH_METRIC_ANGULAR) {
+    normalize_rows_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(xq, n_queries, d, 1e-8f,
+                                                                          w.qn);
+    NLSH_CUDA_TRY(cudaGetLastError());
+    q_used = w.qn;
+  }
+
+  ScanArgs a{};
+  a.xs = x_sorted;
+  a.ids = ids;
+  a.offsets = offsets;
+  a.q = q_used;
+  a.pair_off = w.pair_off;
+  a.pairs = w.pairs;
+  a.item_off = w.item_off;
+  a.item_counter = w.counter;
+  a.part_d = w.part_d;
+  a.part_id = w.part_id;
+  a.n_rows = n_rows;
+  a.self_offset = 0;
+  a.n_queries = (int)n_queries;
+  a.n_buckets = n_buckets;
+  a.p = p;
+  a.k = k;
+  a.rchunk = pol.rchunk;
+  a.max_chunks = pol.max_chunks;
+  a.dense = 0;
+  a.exclude_self = 0;
+  a.d = geom.d;
+  a.d_pad = geom.d_pad;
+  a.dc = geom.dc;
+  a.n_chunks = geom.n_chunks;
+  a.stride_f = geom.stride_f;
+  a.stages = geom.stages;
+  const int grid = nlsh_num_sms() * kCtasPerSm;
+  int rc = launch_scan_metric(metric, a, geom, async, grid, st);
+  if (rc != NLSH_OK) return rc;
+  return launch_merge_partials(w.part_d, w.part_id, probes, offsets, n_buckets, p, k, pol.rchunk,
+                               pol.max_chunks, 0, n_queries, id_offset, ids_out, dists_out,
+                               ncand_out, st);
+}
+
+extern "C" size_t nlsh_knn_workspace_bytes(int64_t n_queries, int64_t n_rows, int32_t d, int32_t k) {
+  if (n_queries < 0 || n_rows < 0 || d < 1 || k < 1) return 0;
+  const KnnPlan kp = knn_plan(n_queries, n_rows);
+  WorkspaceCarver ws(nullptr);
+  ws.take<int>(64);
+  ws.take<float>((size_t)n_queries * d);
+  const size_t lists = (size_t)n_queries * kp.n_blocks * kConsumerWarps * k;
+  ws.take<float>(lists);
+  ws.take<int>(lists);
+  return ws.total();
+}
+
+extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const float* xdb,
+                                   int64_t n_rows, int32_t d, int32_t metric, int32_t k,
+                                   int32_t exclude_self, int64_t self_offset, int64_t id_offset,
+                                   int64_t* ids_out, float* dists_out, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  NLSH_REQUIRE(n_queries >= 0 && n_queries < (1ll << 28), "knn: n_queries=%lld outside [0, 2^28)",
+               (long long)n_queries);
+  NLSH_REQUIRE(n_rows >= 0 && n_rows < (1ll << 31), "knn: n_rows=%lld outside [0, 2^31)",
+               (long long)n_rows);
+  NLSH_REQUIRE(d >= 1 && d <= 16384, "knn: d=%d outside [1, 16384]", d);
+  NLSH_REQUIRE(d % 4 == 0, "knn: d=%d must be a multiple of 4 (pad the rows with zeros)", d);
+  NLSH_REQUIRE(k >= 1 && k <= NLSH_MAX_K, "knn: k=%d outside [1, %d]", k, NLSH_MAX_K);
+  NLSH_REQUIRE(metric >= NLSH_METRIC_L2 && metric <= NLSH_METRIC_COSINE, "knn: unknown metric %d",
+               metric);
+  if (n_queries == 0) return NLSH_OK;
+  NLSH_REQUIRE(xq && ids_out && dists_out, "knn: null pointer");
+  NLSH_REQUIRE(n_rows == 0 || xdb, "knn: xdb is NULL");
+  NLSH_REQUIRE((reinterpret_cast<uintptr_t>(xdb) & 15) == 0, "knn: xdb not 16-byte aligned");
+  const size_t need = nlsh_knn_workspace_bytes(n_queries, n_rows, d, k);
+  if (workspace == nullptr || workspace_bytes < need) {
+    nlsh_set_error("knn: workspace %zu bytes < required %zu", workspace_bytes, need);
+    return NLSH_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const KnnPlan kp = knn_plan(n_queries, n_rows);
+  WorkspaceCarver ws(workspace);
+  int* counter = ws.take<int>(64);
+  float* qn = ws.take<float>((size_t)n_queries * d);
+  const size_t lists = (size_t)n_queries * kp.n_blocks * kConsumerWarps * k;
+  float* part_d = ws.take<float>(lists);
+  int* part_id = ws.take<int>(lists);
+
+  NLSH_CUDA_TRY(cudaMemsetAsync(counter, 0, 64 * sizeof(int), st));
+  const float* q_used = xq;
+  if (metric == NLSH_METRIC_ANGULAR || metric == NLSH_METRIC_COSINE) {
+    normalize_rows_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(
+        xq, n_queries, d, metric == NLSH_METRIC_ANGULAR ? 1e-8f : 0.f, qn);
+    NLSH_CUDA_TRY(cudaGetLastError());
+    q_used = qn;
+  }
+  const ScanGeom geom = scan_geom(d, true);
+  ScanArgs a{};
+  a.xs = xdb;
+  a.ids = nullptr;
+  a.q = q_used;
+  a.item_counter = counter;
+  a.part_d = part_d;
+  a.part_id = part_id;
+  a.n_rows = n_rows;
+  a.self_offset = self_offset;
+  a.n_queries = (int)n_queries;
+  a.n_buckets = 1;
+  a.p = 1;
+  a.k = k;
+  a.rchunk = kp.rchunk;
+  a.max_chunks = kp.n_blocks;
+  a.dense = 1;
+  a.dense_qgroups = kp.qgroups;
+  a.dense_items = n_rows > 0 ? kp.qgroups * kp.n_blocks : 0;
+  a.exclude_self = exclude_self ? 1 : 0;
+  a.d = geom.d;
+  a.d_pad = geom.d_pad;
+  a.dc = geom.dc;
+  a.n_chunks = geom.n_chunks;
+  a.stride_f = geom.stride_f;
+  a.stages = geom.stages;
+  const int grid = nlsh_num_sms() * kCtasPerSm;
+  if (n_rows > 0) {
+    int rc = launch_scan_metric(metric, a, geom, true, grid, st);
+    if (rc != NLSH_OK) return rc;
+  } else {
+    // no rows: every list is empty
+    fill_int_kernel<<<(unsigned)((lists + 255) / 256), 256, 0, st>>>(part_id, lists, NLSH_ID_SENTINEL);
+    NLSH_CUDA_TRY(cudaGetLastError());
+  }
+  return launch_merge_partials(part_d, part_id, nullptr, nullptr, 1, 1, k, kp.rchunk, kp.n_blocks, 1,
+                               n_queries, id_offset, ids_out, dists_out, nullptr, st);
+}
+
+extern "C" int nlsh_merge_topk(const float* dists, const int64_t* ids, int32_t n_lists,
+                               int64_t n_queries, int32_t k, int64_t* ids_out, float* dists_out,
+                               void* stream) {
+  NLSH_REQUIRE(n_lists >= 1 && n_queries >= 0, "merge: bad shape n_lists=%d n_queries=%lld", n_lists,
+               (long long)n_queries);
+  NLSH_REQUIRE(k >= 1 && k <= NLSH_MAX_K, "merge: k=%d outside [1, %d]", k, NLSH_MAX_K);
+  if (n_queries == 0) return NLSH_OK;
+  NLSH_REQUIRE(dists && ids && ids_out && dists_out, "merge: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)((n_queries + 3) / 4);
+  const long long* ids_ll = reinterpret_cast<const long long*>(ids);
+  long long* out_ll = reinterpret_cast<long long*>(ids_out);
+  if (k <= 32)
+    merge_lists_kernel<1><<<blocks, 128, 0, st>>>(dists, ids_ll, n_lists, n_queries, k, out_ll, dists_out);
+  else if (k <= 64)
+    merge_lists_kernel<2><<<blocks, 128, 0, st>>>(dists, ids_ll, n_lists, n_queries, k, out_ll, dists_out);
+  else
+    merge_lists_kernel<4><<<blocks, 128, 0, st>>>(dists, ids_ll, n_lists, n_queries, k, out_ll, dists_out);
+  return nlsh_check_cuda(cudaGetLastError(), "merge_lists_kernel launch");
+}
+
+extern "C" int nlsh_recall_hits(const int64_t* gt, int32_t k_gt, const int64_t* pred, int32_t k_pred,
+                                int64_t n_queries, int32_t* hits_out, void* stream) {
+  NLSH_REQUIRE(k_gt >= 1 && k_pred >= 1 && n_queries >= 0, "recall: bad shape");
+  if (n_queries == 0) return NLSH_OK;
+  NLSH_REQUIRE(gt && pred && hits_out, "recall: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  recall_hits_kernel<<<(unsigned)((n_queries + 127) / 128), 128, 0, st>>>(
+      reinterpret_cast<const long long*>(gt), k_gt, reinterpret_cast<const long long*>(pred), k_pred,
+      n_queries, hits_out);
+  return nlsh_check_cuda(cudaGetLastError(), "recall_hits_kernel launch");
+}

@@ -1,0 +1,70 @@
+"""The C-ABI library: loads, exports every symbol include/nlsh_b200.h declares, and its
+host-only entry points work without a GPU.  No device compute here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "nlsh_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nlsh_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from nlsh import _native
+    assert os.path.exists(_native.LIB_PATH), "build the library: make -C neural-locality-sensitive-hashing_b200"
+    handle = ctypes.CDLL(_native.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in nlsh_b200.h but not exported"
+    # and the Python binding covers exactly the header
+    assert sorted(_native.PROTOTYPES) == names
+
+
+def test_version_and_error_string():
+    from nlsh import _native
+    assert _native.lib().nlsh_version() == 100
+    assert isinstance(_native.last_error(), str)
+
+
+def test_argument_validation_without_gpu():
+    from nlsh import _native
+    L = _native.lib()
+    # invalid arguments are rejected before any CUDA call is made
+    assert L.nlsh_topp_probes(None, 4, 40, _native.HEAD_SIGMOID, 2, None, None) == _native.ERR_INVALID
+    assert "hash_size" in _native.last_error()
+    assert L.nlsh_query_scan_topk(None, 1, 8, None, 1, None, 4, None, None, 0, 0, 7, 10, 0, None,
+                                  None, None, None, 0, 0, None) == _native.ERR_INVALID
+    assert "metric" in _native.last_error()
+    assert L.nlsh_build_csr(None, -1, 4, None, 0, None, None, None, None, 0, None) == _native.ERR_INVALID
+    assert L.nlsh_build_workspace_bytes(1000, 16) > 0
+    assert L.nlsh_query_workspace_bytes(100, 4, 10, 128, 256, 10000, 100) > 0
+    assert L.nlsh_knn_workspace_bytes(100, 1000, 128, 10) > 0
+
+
+def test_pack_codes_host_matches_reference(golden, oracle):
+    from nlsh.utils import hash_codes
+    for name in ("hc", "hc_wide", "hc_strided"):
+        bits = golden[f"{name}_bits"]
+        want = [set(int(v) for v in row if v != -32768) for row in golden[f"{name}_codes"]]
+        assert hash_codes(bits) == want
+    view = np.random.RandomState(0).randint(0, 2, size=(9, 6, 14)).astype(np.intc)[::2, 1::2, ::3]
+    assert hash_codes(view) == oracle.hash_codes(np.ascontiguousarray(view))
+    assert hash_codes(np.ones((1, 1, 16), dtype=np.intc)) == [{-1}]
+    assert hash_codes(np.zeros((0, 1, 4), dtype=np.intc)) == []
+
+
+def test_hash_codes_error_behaviour():
+    # Cython buffer-protocol errors of utils.pyx:19 are ValueErrors
+    from nlsh.utils import hash_codes
+    with pytest.raises(ValueError):
+        hash_codes(np.ones((2, 2, 4), dtype=np.int64))
+    with pytest.raises(ValueError):
+        hash_codes(np.ones((2, 4), dtype=np.intc))

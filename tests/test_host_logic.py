@@ -1,0 +1,131 @@
+"""Host-side logic of the drop-in package that needs no GPU."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def test_resolve_metric():
+    from nlsh import _native
+    from nlsh.indexer import resolve_metric
+
+    class SIFT:
+        @staticmethod
+        def distance(v1, v2):
+            return F.pairwise_distance(v1, v2)
+
+    class Glove:
+        @staticmethod
+        def distance(v1, v2):
+            return 1 - F.cosine_similarity(v1, v2, dim=-1)
+
+    assert resolve_metric(F.pairwise_distance) == _native.METRIC_L2
+    assert resolve_metric(SIFT.distance) == _native.METRIC_L2
+    assert resolve_metric(Glove.distance) == _native.METRIC_ANGULAR
+    assert resolve_metric(lambda a, b: 1 - F.cosine_similarity(a, b, dim=-1)) == _native.METRIC_ANGULAR
+    assert resolve_metric(lambda a, b: F.pairwise_distance(a, b)) == _native.METRIC_L2
+    assert resolve_metric(None, "angular") == _native.METRIC_ANGULAR
+    assert resolve_metric("l2") == _native.METRIC_L2
+    with pytest.raises(ValueError):  # squared L2 is not the scan metric: refused, no fallback
+        resolve_metric(lambda a, b: ((a - b) ** 2).sum(-1))
+    with pytest.raises(ValueError):
+        resolve_metric(None, "manhattan")
+
+
+def test_extract_layer_tensors_matches_module_forward(oracle):
+    from encoders import MultiLayerRelu, TwoLayer256Relu
+    from nlsh import _native
+    from nlsh.hashings import extract_layer_tensors
+    torch.manual_seed(0)
+    x = torch.randn(17, 12)
+    for enc in (MultiLayerRelu(12, [16, 8]), MultiLayerRelu(12, [16, 8], with_batchnorm=True),
+                MultiLayerRelu(12, [16], with_bias=False), TwoLayer256Relu(12)):
+        out = nn.Linear(enc.output_dim, 5)
+        for m in enc.modules():
+            if isinstance(m, nn.BatchNorm1d):
+                m.running_mean.normal_()
+                m.running_var.uniform_(0.5, 2.0)
+                m.weight.data.normal_()
+                m.bias.data.normal_()
+        enc.eval()
+        layers = [oracle.Layer(w, b, act == _native.ACT_RELU) for w, b, act in extract_layer_tensors(enc, out)]
+        with torch.no_grad():
+            want = out(enc(x))
+        torch.testing.assert_close(oracle.mlp_logits(x, layers), want, rtol=1e-5, atol=1e-5)
+
+
+def test_extract_layers_refuses_unknown_modules():
+    from nlsh.hashings import extract_layer_tensors
+    enc = nn.Sequential(nn.Linear(4, 4), nn.GELU())
+    with pytest.raises(NotImplementedError):
+        extract_layer_tensors(enc, nn.Linear(4, 2))
+    bn = nn.Sequential(nn.Linear(4, 4), nn.BatchNorm1d(4))
+    bn.train()
+    with pytest.raises(NotImplementedError):
+        extract_layer_tensors(bn, nn.Linear(4, 2))
+
+
+def test_hashing_api_surface_and_loud_failure_without_cuda():
+    from encoders import MultiLayerRelu
+    from nlsh import _native
+    from nlsh.hashings import MultivariateBernoulli, Categorical
+    h = MultivariateBernoulli(MultiLayerRelu(8, [16]), 6, F.pairwise_distance)
+    assert h.output_dim == 6 and h.n_buckets == 64 and h.distance is F.pairwise_distance
+    assert len(list(h.parameters())) == 4
+    h.train_mode(False)
+    assert not h._hasher.training
+    if not torch.cuda.is_available():
+        assert h.predict(torch.randn(3, 8)).shape == (3, 6)
+        with pytest.raises(_native.NativeLibraryError):
+            h.hash(torch.randn(3, 8))  # CPU tensors: no fallback
+    with pytest.raises(ValueError):
+        h.hash(torch.randn(3, 8), n=0)
+    c = Categorical(MultiLayerRelu(8, [16]), 10, None)
+    assert c.n_buckets == 10 and c.head == _native.HEAD_SOFTMAX
+
+
+def test_bucket_view():
+    from nlsh.indexer import BucketView
+    off = np.array([0, 2, 2, 5, 6], dtype=np.int64)
+    ids = torch.tensor([3, 9, 0, 4, 7, 1], dtype=torch.int32)
+    view = BucketView(off, ids)
+    assert len(view) == 3 and list(view.keys()) == [0, 2, 3]
+    assert [len(v) for v in view.values()] == [2, 3, 1]
+    assert view[2].tolist() == [0, 4, 7] and view[2].dtype == torch.int64
+    assert view.get(1, "empty") == "empty" and 1 not in view and 2 in view
+    assert dict(view.items())[3].tolist() == [1]
+    assert view.sizes.tolist() == [2, 3, 1]
+    assert BucketView(off, ids, id_offset=100)[0].tolist() == [103, 109]
+
+
+def test_probes_from_sets_and_shard_range():
+    from nlsh.indexer import Indexer
+    from nlsh.parallel import shard_range
+    pr = Indexer.probes_from_sets([{1, 2}, {7}, set()], "cpu", width=3)
+    assert pr.shape == (3, 3) and sorted(pr[0].tolist()) == [-1, 1, 2] and pr[2].tolist() == [-1, -1, -1]
+    for n, w in [(10, 3), (7, 8), (1000003, 8), (16, 4)]:
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_recall_functions_match_reference_values(golden):
+    from nlsh.metrics import calculate_recall
+    yt, yp = golden["recall_true"].tolist(), golden["recall_pred"].tolist()
+    assert calculate_recall(yt, yp) == golden["recall_values"].tolist()
+    assert calculate_recall(yt, yp, np.mean) == pytest.approx(float(golden["recall_mean"]))
+
+
+def test_precompute_metric_resolution():
+    import precompute
+    from nlsh import _native
+    assert precompute._resolve_knn_metric(precompute._l2) == _native.METRIC_L2SQ
+    assert precompute._resolve_knn_metric(precompute._cosine_distance) == _native.METRIC_COSINE
+    assert precompute._resolve_knn_metric("angular") == _native.METRIC_ANGULAR
+    with pytest.raises(ValueError):
+        precompute._resolve_knn_metric(lambda a, b: a @ b.T)
+    a, b = torch.randn(5, 7), torch.randn(6, 7)
+    torch.testing.assert_close(precompute._l2(a, b), torch.cdist(a, b) ** 2, rtol=1e-4, atol=1e-4)
