@@ -185,6 +185,17 @@ int nlsh_merge_topk(const float* dists, const int64_t* ids, int32_t n_lists, int
 int nlsh_recall_hits(const int64_t* gt, int32_t k_gt, const int64_t* pred, int32_t k_pred,
                      int64_t n_queries, int32_t* hits_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): number of kernels this library has launched in the
+ * process, and a ring of CUDA-event pairs recorded on the launching stream around the
+ * candidate-scan kernel of every nlsh_query_scan_topk call while enabled (per thread, up to
+ * 256 calls).  nlsh_profile_read waits for the events, writes the kernel durations in ms,
+ * returns how many it wrote (or a negative error) and rewinds the ring.
+ * ------------------------------------------------------------------------------------- */
+long long nlsh_kernel_launch_count(void);
+int nlsh_profile_enable(int on);
+int nlsh_profile_read(float* ms_out, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 static thread_local char g_last_error[512] = "";
@@ -33,6 +35,61 @@ int nlsh_num_sms() {
     cached_sms = sms;
   }
   return cached_sms;
+}
+
+static std::atomic<long long> g_launches{0};
+
+cudaError_t nlsh_post_launch() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+extern "C" long long nlsh_kernel_launch_count(void) { return g_launches.load(); }
+
+// ---- scan-kernel timing: a ring of CUDA event pairs recorded on the launching stream ------
+namespace {
+constexpr int kProfileSlots = 256;
+struct ProfileRing {
+  cudaEvent_t begin[kProfileSlots];
+  cudaEvent_t end[kProfileSlots];
+  int created = 0;
+  int count = 0;
+  bool enabled = false;
+};
+thread_local ProfileRing g_prof;
+}  // namespace
+
+void nlsh_profile_mark(cudaStream_t st, bool begin) {
+  if (!g_prof.enabled || g_prof.count >= kProfileSlots) return;
+  if (g_prof.created <= g_prof.count) {
+    cudaEventCreate(&g_prof.begin[g_prof.count]);
+    cudaEventCreate(&g_prof.end[g_prof.count]);
+    g_prof.created = g_prof.count + 1;
+  }
+  if (begin) {
+    cudaEventRecord(g_prof.begin[g_prof.count], st);
+  } else {
+    cudaEventRecord(g_prof.end[g_prof.count], st);
+    ++g_prof.count;
+  }
+}
+
+extern "C" int nlsh_profile_enable(int on) {
+  g_prof.enabled = on != 0;
+  g_prof.count = 0;
+  return NLSH_OK;
+}
+
+extern "C" int nlsh_profile_read(float* ms_out, int capacity) {
+  int n = g_prof.count < capacity ? g_prof.count : capacity;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(g_prof.end[i]) != cudaSuccess) return NLSH_ERR_CUDA;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof.begin[i], g_prof.end[i]) != cudaSuccess) return NLSH_ERR_CUDA;
+    ms_out[i] = ms;
+  }
+  g_prof.count = 0;
+  return n;
 }
 
 extern "C" int nlsh_version(void) { return NLSH_B200_VERSION; }

@@ -267,21 +267,21 @@ extern "C" int nlsh_build_csr(const int32_t* codes, int64_t n, int32_t n_buckets
   if (n > 0) {
     unit_hist_kernel<<<unit_blocks, 128, 0, st>>>(codes, n, n_buckets, p.n_units, p.rows_per_unit,
                                                   hist);
-    NLSH_CUDA_TRY(cudaGetLastError());
+    NLSH_CUDA_TRY(nlsh_post_launch());
   }
   scan_reduce_kernel<<<(unsigned)p.n_scan_blocks, kScanThreads, 0, st>>>(hist, block_sums);
-  NLSH_CUDA_TRY(cudaGetLastError());
+  NLSH_CUDA_TRY(nlsh_post_launch());
   scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, p.n_scan_blocks);
-  NLSH_CUDA_TRY(cudaGetLastError());
+  NLSH_CUDA_TRY(nlsh_post_launch());
   scan_apply_kernel<<<(unsigned)p.n_scan_blocks, kScanThreads, 0, st>>>(hist, block_sums);
-  NLSH_CUDA_TRY(cudaGetLastError());
+  NLSH_CUDA_TRY(nlsh_post_launch());
   extract_offsets_kernel<<<(n_buckets + 1 + 255) / 256, 256, 0, st>>>(
       hist, p.n_units, n_buckets, block_sums + p.n_scan_blocks, offsets_out);
-  NLSH_CUDA_TRY(cudaGetLastError());
+  NLSH_CUDA_TRY(nlsh_post_launch());
   if (n > 0) {
     unit_scatter_kernel<<<unit_blocks, 128, 0, st>>>(codes, n, n_buckets, p.n_units,
                                                      p.rows_per_unit, hist, ids_out);
-    NLSH_CUDA_TRY(cudaGetLastError());
+    NLSH_CUDA_TRY(nlsh_post_launch());
     if (x_sorted_out != nullptr) {
       const int sms = nlsh_num_sms();
       const long long warps_needed = (n + 3) / 4;
@@ -294,7 +294,7 @@ extern "C" int nlsh_build_csr(const int32_t* codes, int64_t n, int32_t n_buckets
         gather_rows_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(x, ids_out, n, d, x_sorted_out);
       else
         gather_rows_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(x, ids_out, n, d, x_sorted_out);
-      NLSH_CUDA_TRY(cudaGetLastError());
+      NLSH_CUDA_TRY(nlsh_post_launch());
     }
   }
   return NLSH_OK;

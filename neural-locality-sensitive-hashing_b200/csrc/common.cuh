@@ -12,6 +12,10 @@
 // ---- error plumbing (api.cu) -----------------------------------------------------------
 void nlsh_set_error(const char* fmt, ...);
 int nlsh_check_cuda(cudaError_t e, const char* what);
+// cudaGetLastError() after a kernel launch; also counts the launch (nlsh_kernel_launch_count)
+cudaError_t nlsh_post_launch();
+// optional CUDA-event bracket around the scan kernel (nlsh_profile_*), api.cu
+void nlsh_profile_mark(cudaStream_t st, bool begin);
 
 #define NLSH_CUDA_TRY(expr)                                  \
   do {                                                       \
@@ -180,7 +184,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait suspends the thread in hardware for a bounded time; a pipeline that never
+  // completes traps (-> CUDA error on the host) instead of hanging the device.
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++polls > (1u << 24)) __trap();
   }
 }
 // global -> shared bulk copy (SASS UBLKCP), completion counted in bytes on `bar`.

@@ -300,7 +300,7 @@ int launch_linear(const float* A, int lda, const nlsh_layer_t& L, float* C, int 
     linear_act_kernel<128, 128, 8, 8><<<grid, 256, 0, st>>>(A, lda, L.weight, L.bias, C, ldc, M, N,
                                                            K, L.act, L.act_scale, vec_ok);
   }
-  return nlsh_check_cuda(cudaGetLastError(), "linear_act_kernel launch");
+  return nlsh_check_cuda(nlsh_post_launch(), "linear_act_kernel launch");
 }
 
 }  // namespace
@@ -329,7 +329,7 @@ extern "C" int nlsh_codes_from_logits(const float* logits, int64_t n, int32_t ha
   const int threads = 256;
   const long long blocks = (n + threads - 1) / threads;
   codes_kernel<<<(unsigned)blocks, threads, 0, st>>>(logits, n, hash_size, head, codes_out);
-  return nlsh_check_cuda(cudaGetLastError(), "codes_kernel launch");
+  return nlsh_check_cuda(nlsh_post_launch(), "codes_kernel launch");
 }
 
 extern "C" int nlsh_mlp_hash_f32(const float* x, int64_t n, int32_t d, const nlsh_layer_t* layers,
@@ -408,5 +408,5 @@ extern "C" int nlsh_topp_probes(const float* logits, int64_t n, int32_t hash_siz
     else
       probes_bernoulli_kernel<4><<<blocks, 128, 0, st>>>(logits, n, hash_size, head, p, probes_out);
   }
-  return nlsh_check_cuda(cudaGetLastError(), "probes kernel launch");
+  return nlsh_check_cuda(nlsh_post_launch(), "probes kernel launch");
 }

@@ -664,7 +664,7 @@ int launch_scan(const ScanArgs& a, const ScanGeom& g, bool async, int grid, cuda
                                        (int)g.smem_bytes));
     kern<<<grid, 32 * kConsumerWarps, g.smem_bytes, st>>>(a);
   }
-  return nlsh_check_cuda(cudaGetLastError(), "scan_kernel launch");
+  return nlsh_check_cuda(nlsh_post_launch(), "scan_kernel launch");
 }
 
 template <int METRIC>
@@ -702,7 +702,7 @@ int launch_merge_partials(const float* part_d, const int* part_id, const int* pr
     merge_partials_kernel<4><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
                                                      k, rchunk, max_chunks, dense, n_queries,
                                                      id_offset, ids_ll, dists_out, ncand_out);
-  return nlsh_check_cuda(cudaGetLastError(), "merge_partials_kernel launch");
+  return nlsh_check_cuda(nlsh_post_launch(), "merge_partials_kernel launch");
 }
 
 struct QueryWorkspace {
@@ -811,19 +811,19 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   NLSH_CUDA_TRY(cudaMemsetAsync(w.cnt, 0, w.zero_ints * sizeof(int), st));
   plan_count_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(probes, offsets, n_buckets, p,
                                                                      n_pairs, w.cnt);
-  NLSH_CUDA_TRY(cudaGetLastError());
+  NLSH_CUDA_TRY(nlsh_post_launch());
   plan_scan_kernel<<<1, 1024, 0, st>>>(w.cnt, offsets, n_buckets, pol.rchunk, pol.max_chunks,
                                        w.pair_off, w.item_off);
-  NLSH_CUDA_TRY(cudaGetLastError());
+  NLSH_CUDA_TRY(nlsh_post_launch());
   plan_scatter_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(
       probes, offsets, n_buckets, p, n_pairs, w.pair_off, w.cursor, w.pairs);
-  NLSH_CUDA_TRY(cudaGetLastError());
+  NLSH_CUDA_TRY(nlsh_post_launch());
 
   const float* q_used = xq;
   if (metric == NLSH_METRIC_ANGULAR) {
     normalize_rows_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(xq, n_queries, d, 1e-8f,
                                                                           w.qn);
-    NLSH_CUDA_TRY(cudaGetLastError());
+    NLSH_CUDA_TRY(nlsh_post_launch());
     q_used = w.qn;
   }
 
@@ -855,7 +855,9 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   a.stride_f = geom.stride_f;
   a.stages = geom.stages;
   const int grid = nlsh_num_sms() * kCtasPerSm;
+  nlsh_profile_mark(st, true);
   int rc = launch_scan_metric(metric, a, geom, async, grid, st);
+  nlsh_profile_mark(st, false);
   if (rc != NLSH_OK) return rc;
   return launch_merge_partials(w.part_d, w.part_id, probes, offsets, n_buckets, p, k, pol.rchunk,
                                pol.max_chunks, 0, n_queries, id_offset, ids_out, dists_out,
@@ -911,7 +913,7 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
   if (metric == NLSH_METRIC_ANGULAR || metric == NLSH_METRIC_COSINE) {
     normalize_rows_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(
         xq, n_queries, d, metric == NLSH_METRIC_ANGULAR ? 1e-8f : 0.f, qn);
-    NLSH_CUDA_TRY(cudaGetLastError());
+    NLSH_CUDA_TRY(nlsh_post_launch());
     q_used = qn;
   }
   const ScanGeom geom = scan_geom(d, true);
@@ -947,7 +949,7 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
   } else {
     // no rows: every list is empty
     fill_int_kernel<<<(unsigned)((lists + 255) / 256), 256, 0, st>>>(part_id, lists, NLSH_ID_SENTINEL);
-    NLSH_CUDA_TRY(cudaGetLastError());
+    NLSH_CUDA_TRY(nlsh_post_launch());
   }
   return launch_merge_partials(part_d, part_id, nullptr, nullptr, 1, 1, k, kp.rchunk, kp.n_blocks, 1,
                                n_queries, id_offset, ids_out, dists_out, nullptr, st);
@@ -971,7 +973,7 @@ extern "C" int nlsh_merge_topk(const float* dists, const int64_t* ids, int32_t n
     merge_lists_kernel<2><<<blocks, 128, 0, st>>>(dists, ids_ll, n_lists, n_queries, k, out_ll, dists_out);
   else
     merge_lists_kernel<4><<<blocks, 128, 0, st>>>(dists, ids_ll, n_lists, n_queries, k, out_ll, dists_out);
-  return nlsh_check_cuda(cudaGetLastError(), "merge_lists_kernel launch");
+  return nlsh_check_cuda(nlsh_post_launch(), "merge_lists_kernel launch");
 }
 
 extern "C" int nlsh_recall_hits(const int64_t* gt, int32_t k_gt, const int64_t* pred, int32_t k_pred,
@@ -983,5 +985,5 @@ extern "C" int nlsh_recall_hits(const int64_t* gt, int32_t k_gt, const int64_t* 
   recall_hits_kernel<<<(unsigned)((n_queries + 127) / 128), 128, 0, st>>>(
       reinterpret_cast<const long long*>(gt), k_gt, reinterpret_cast<const long long*>(pred), k_pred,
       n_queries, hits_out);
-  return nlsh_check_cuda(cudaGetLastError(), "recall_hits_kernel launch");
+  return nlsh_check_cuda(nlsh_post_launch(), "recall_hits_kernel launch");
 }

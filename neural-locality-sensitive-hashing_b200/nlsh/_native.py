@@ -65,6 +65,9 @@ PROTOTYPES = {
                                            _vp, _vp, _vp, _sz, _vp]),
     "nlsh_merge_topk": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "nlsh_recall_hits": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i64, _vp, _vp]),
+    "nlsh_kernel_launch_count": (ctypes.c_longlong, []),
+    "nlsh_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "nlsh_profile_read": (ctypes.c_int, [_vp, ctypes.c_int]),
 }
 
 _lib = None
@@ -353,3 +356,23 @@ def recall_hits(gt, pred):
                                     _stream())
     _check(rc, "nlsh_recall_hits")
     return hits
+
+
+# --------------------------------------------------------------------------------------
+# measurement hooks
+# --------------------------------------------------------------------------------------
+def kernel_launch_count():
+    return int(lib().nlsh_kernel_launch_count())
+
+
+def profile_enable(on=True):
+    lib().nlsh_profile_enable(1 if on else 0)
+
+
+def profile_read(capacity=256):
+    """Durations (ms) of the scan kernels recorded since profile_enable / the last read."""
+    buf = (ctypes.c_float * capacity)()
+    n = lib().nlsh_profile_read(ctypes.cast(buf, ctypes.c_void_p), capacity)
+    if n < 0:
+        raise RuntimeError("nlsh_profile_read failed")
+    return [float(buf[i]) for i in range(n)]

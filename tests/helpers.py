@@ -40,3 +40,38 @@ def assert_topk_equal_up_to_ties(got_ids, got_d, ref_ids, ref_d, rtol=1e-5, atol
             at_boundary = abs(rd[pos] - rd[-1]) <= tol[pos]
             assert tied_inside or at_boundary, \
                 f"query {q} pos {pos}: id {a} vs {b} without a distance tie ({gd} vs {rd})"
+
+
+def hashing_from_golden(golden, prefix, cls="bernoulli"):
+    """A nlsh.hashings object carrying the golden case's weights (on the GPU)."""
+    import torch
+    from encoders import MultiLayerRelu
+    from nlsh.hashings import MultivariateBernoulli, Categorical
+    n = int(golden[f"{prefix}_n_layers"])
+    dims = [golden[f"{prefix}_w{i}"].shape for i in range(n)]
+    enc = MultiLayerRelu(dims[0][1], [s[0] for s in dims[:-1]])
+    if cls == "categorical":
+        h = Categorical(enc, dims[-1][0], None)
+    else:
+        h = MultivariateBernoulli(enc, dims[-1][0], None, tanh_output=bool(int(golden.get(f"{prefix}_tanh", 0))))
+    linears = [m for m in h._hasher._encoder.children() if isinstance(m, torch.nn.Linear)]
+    linears.append(h._hasher.output_layer)
+    with torch.no_grad():
+        for i, lin in enumerate(linears):
+            lin.weight.copy_(torch.from_numpy(golden[f"{prefix}_w{i}"]))
+            lin.bias.copy_(torch.from_numpy(golden[f"{prefix}_b{i}"]))
+    h.train_mode(False)
+    return h
+
+
+def oracle_layers_from_hashing(hashing, oracle):
+    from nlsh.hashings import extract_layer_tensors
+    return [oracle.Layer(w.cpu(), None if b is None else b.cpu(), act == 1)
+            for w, b, act in extract_layer_tensors(hashing._hasher._encoder, hashing._hasher.output_layer)]
+
+
+def mixture(n, d, n_centers, seed, spread=2.0, noise=1.0):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    centers = torch.randn(n_centers, d, generator=g) * spread
+    return centers[torch.randint(0, n_centers, (n,), generator=g)] + noise * torch.randn(n, d, generator=g)

@@ -1,0 +1,139 @@
+"""End-to-end drop-in checks on the GPU: the call sequence of nlsh/trainers/base.py:80-115
+against the oracle's CPU flow, the sharded search, and BASELINE-size properties."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import assert_topk_equal_up_to_ties, mixture, oracle_layers_from_hashing
+
+pytestmark = pytest.mark.gpu
+
+
+def test_trainer_validation_block_flow(oracle):
+    # what Trainer.fit does every test_every_updates steps (base.py:80-115)
+    from encoders import MultiLayerRelu
+    from nlsh.hashings import MultivariateBernoulli
+    from nlsh.indexer import Indexer
+    from nlsh.metrics import calculate_recall
+    import precompute
+    torch.manual_seed(3)
+    n, d, hs, nq, K = 30000, 64, 6, 500, 10
+    X = mixture(n, d, 256, seed=11)
+    Qv = mixture(nq, d, 256, seed=11) + 0.05 * torch.randn(nq, d, generator=torch.Generator().manual_seed(1))
+    hashing = MultivariateBernoulli(MultiLayerRelu(d, [64, 64]), hs, F.pairwise_distance)
+    hashing.train_mode(False)
+    indexer = Indexer(hashing, X.cuda(), F.pairwise_distance)
+    n_indexes = len(indexer.index2row)
+    std_index_rows = np.std([len(idxs) for idxs in indexer.index2row.values()])
+    assert 1 <= n_indexes <= 64 and std_index_rows >= 0
+    assert sum(len(v) for v in indexer.index2row.values()) == n
+    recalls, n_candidates = indexer.query(Qv.cuda(), k=K, hash_times=1)
+    gt, _ = precompute.knn_tensors(Qv.cuda(), X.cuda(), "l2", K)
+    current_recall = calculate_recall(gt.cpu().tolist(), recalls, np.mean)
+    # the same flow on the CPU through the oracle, from the same weights
+    layers = oracle_layers_from_hashing(hashing, oracle)
+    cpu = oracle.CpuIndexer(layers, oracle.HEAD_SIGMOID, X, "l2")
+    c_ids, c_ncand = cpu.query(Qv, k=K)
+    agree = np.mean([a == b for a, b in zip(n_candidates, c_ncand)])
+    assert agree >= 0.99  # a query lands in another bucket only if a logit sits at a rounding tie
+    same = [i for i in range(nq) if n_candidates[i] == c_ncand[i] and c_ncand[i] >= K]
+    assert np.mean([recalls[i] == c_ids[i] for i in same]) >= 0.99
+    o_gt, _ = oracle.knn_queries(Qv, X, "l2", K)
+    cpu_recall = oracle.recall(o_gt.tolist(), c_ids)
+    assert abs(current_recall - cpu_recall) < 2e-3
+    assert 0.0 < current_recall <= 1.0
+
+
+def test_sharded_search_equals_single_index(oracle):
+    # emulate G shards in one process (gloo covers the collective plumbing on the CPU, the
+    # driver's N-GPU bench the NCCL path): per-shard Indexer with id_offset + merge kernel
+    from encoders import MultiLayerRelu
+    from nlsh import _native
+    from nlsh.hashings import MultivariateBernoulli
+    from nlsh.indexer import Indexer
+    from nlsh.parallel import shard_range
+    torch.manual_seed(5)
+    n, d, hs, nq, k, p = 40001, 32, 6, 300, 10, 3
+    X = mixture(n, d, 200, seed=21).cuda()
+    Q = mixture(nq, d, 200, seed=21).cuda()
+    hashing = MultivariateBernoulli(MultiLayerRelu(d, [32]), hs, None)
+    hashing.train_mode(False)
+    full = Indexer(hashing, X, None, metric="l2")
+    f_ids, f_d, f_n = full.query_tensors(Q, k=k, hash_times=p)
+    for G in (2, 4, 8):
+        parts = []
+        for r in range(G):
+            lo, hi = shard_range(n, r, G)
+            shard = Indexer(hashing, X[lo:hi], None, metric="l2", id_offset=lo)
+            parts.append(shard.query_tensors(Q, k=k, hash_times=p))
+        g_ids = torch.stack([t[0] for t in parts])
+        g_d = torch.stack([t[1] for t in parts])
+        m_ids, m_d = _native.merge_topk(g_d, g_ids)
+        assert torch.equal(m_ids, f_ids) and torch.equal(m_d, f_d)
+        assert torch.equal(sum(t[2] for t in parts), f_n)
+        o_ids, o_d = oracle.merge_topk(g_d.cpu().numpy(), g_ids.cpu().numpy(), k)
+        assert np.array_equal(o_ids, m_ids.cpu().numpy())
+
+
+@pytest.mark.parametrize("k", [1, 10, 33, 100, 128])
+def test_merge_kernel_against_oracle(oracle, k):
+    from nlsh import _native
+    g = torch.Generator().manual_seed(k)
+    G, nq = 5, 77
+    d = torch.rand(G, nq, k, generator=g).sort(dim=2)[0]
+    d[:, :, k // 2:] = torch.round(d[:, :, k // 2:] * 8) / 8  # force cross-list ties
+    d = d.sort(dim=2)[0]
+    ids = torch.randint(0, 1 << 40, (G, nq, k), generator=g)
+    ids[2, :, k - k // 3:] = -1  # short lists
+    d[2, :, k - k // 3:] = float("inf")
+    ids[4, 5] = -1
+    d[4, 5] = float("inf")
+    m_ids, m_d = _native.merge_topk(d.cuda(), ids.cuda())
+    o_ids, o_d = oracle.merge_topk(d.numpy(), ids.numpy(), k)
+    assert np.array_equal(m_ids.cpu().numpy(), o_ids)
+    assert np.array_equal(m_d.cpu().numpy(), o_d)
+
+
+def test_full_size_properties_config2():
+    # BASELINE config 2 at full size (1M x 128, 256 buckets, p in {1, 4, 16}, k = 10), checked
+    # through size-independent properties: candidates counted exactly, more probes never hurt,
+    # every returned id is a true candidate with the exact distance, recall monotone in p and
+    # equal to 1 when every bucket is probed.
+    from encoders import MultiLayerRelu
+    from nlsh.hashings import MultivariateBernoulli
+    from nlsh.indexer import Indexer
+    from nlsh.metrics import recall_at_k_tensors
+    import precompute
+    torch.manual_seed(7)
+    n, d, hs, nq, k = 1_000_000, 128, 8, 2000, 10
+    g = torch.Generator(device="cuda").manual_seed(1002)
+    centers = torch.randn(1024, d, generator=g, device="cuda") * 2
+    X = centers[torch.randint(0, 1024, (n,), generator=g, device="cuda")] + torch.randn(n, d, generator=g, device="cuda")
+    Q = centers[torch.randint(0, 1024, (nq,), generator=g, device="cuda")] + torch.randn(nq, d, generator=g, device="cuda")
+    hashing = MultivariateBernoulli(MultiLayerRelu(d, [256, 256]), hs, F.pairwise_distance)
+    hashing.train_mode(False)
+    idx = Indexer(hashing, X, F.pairwise_distance)
+    assert int(idx.bucket_sizes.sum()) == n
+    gt, gt_d = precompute.knn_tensors(Q, X, "l2", k)
+    sizes = torch.from_numpy(idx.bucket_sizes).cuda()
+    prev_recall, prev_d = -1.0, None
+    for p in (1, 4, 16):
+        probes = idx.hash_tensors(Q, p)
+        ids, dists, ncand = idx.query_tensors(Q, k=k, probes=probes)
+        assert torch.equal(ncand.long(), sizes[probes.long()].sum(1))
+        assert (ids >= 0).all()
+        exact = F.pairwise_distance(Q[:, None, :].expand(-1, k, -1).reshape(-1, d), X[ids.reshape(-1)]).view(nq, k)
+        torch.testing.assert_close(dists, exact, rtol=1e-5, atol=0)
+        codes_of_ids = idx._hashing.hash_tensors(X[ids.reshape(-1)], 1)[0].view(nq, k)
+        assert (codes_of_ids[:, :, None] == probes[:, None, :]).any(-1).all()
+        rec = recall_at_k_tensors(gt, ids)
+        assert rec >= prev_recall - 1e-9
+        if prev_d is not None:
+            assert (dists <= prev_d * (1 + 1e-6)).all()
+        prev_recall, prev_d = rec, dists
+    all_probes = torch.arange(256, dtype=torch.int32, device="cuda")[None, :].expand(64, -1).contiguous()
+    ids, dists, ncand = idx.query_tensors(Q[:64], k=k, probes=all_probes)
+    assert (ncand == n).all()
+    torch.testing.assert_close(dists, gt_d[:64], rtol=1e-5, atol=0)
+    assert recall_at_k_tensors(gt[:64], ids) >= 0.999
