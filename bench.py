@@ -297,14 +297,32 @@ def run_b200(args):
     for _ in range(prof_steps):
         _, _, ncand_local = index.local.query_tensors(Q, k=k, hash_times=p_used)
     scan_ms = _native.profile_read()
+    # the same kernel where no bucket tile is shared between queries (about one probing query
+    # per two buckets): every candidate byte has to come from HBM, so this is the figure to
+    # hold against the HBM roofline
+    n_lr = max(8, min(nq, (1 << hs) // (2 * p_used)))
+    for _ in range(3):
+        index.local.query_tensors(Q[:n_lr], k=k, hash_times=p_used)
+    _native.profile_read()
+    lr_steps = 50
+    for _ in range(lr_steps):
+        _, _, ncand_lr = index.local.query_tensors(Q[:n_lr], k=k, hash_times=p_used)
+    lr_ms = _native.profile_read()
     _native.profile_enable(False)
     clocks = sampler.stop()
+    lr_bytes = float(ncand_lr.double().sum().item()) * (4 * d + 4) + n_lr * (4 * d + 8 * k)
+    lr_avg_ms = float(np.mean(lr_ms)) if lr_ms else float("nan")
     algo_bytes = float(ncand_local.double().sum().item()) * (4 * d + 4) + nq * (4 * d + 8 * k)
     scan_avg_ms = float(np.mean(scan_ms)) if scan_ms else float("nan")
     peaks, peak_kind = load_peaks()
     achieved = algo_bytes / (scan_avg_ms * 1e-3) / 1e9
     mean_cand = float(ncand_local.double().mean().item())
 
+    traffic = None
+    prof_path = os.path.join(ROOT, "profiles", "ncu_scan_traffic.json")
+    if os.path.exists(prof_path):
+        rec = json.load(open(prof_path)).get(f"{args.workload}/p{p_used}/gpus{world}")
+        traffic = rec["dram_bytes_per_launch"] if rec else None
     qps = nq * args.steps / (ms * 1e-3)
     e2e_qps = nq * args.steps / (e2e_ms * 1e-3)
     line = {
@@ -327,11 +345,20 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "scan_kernel (candidate scan + top-k)", "achieved": achieved,
                      "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": scan_avg_ms,
                      "kernel_share_of_step": scan_avg_ms / (ms / args.steps),
                      "note": "algorithmic bytes count every (query, candidate) pair; a bucket tile "
-                             "shared by several queries is fetched once, so achieved may exceed peak"},
+                             "shared by several queries is fetched once, so achieved may exceed peak",
+                     "fp32_lane_ops_frac": (float(ncand_local.double().sum().item()) * d * (3 if metric == "l2" else 1))
+                     / (scan_avg_ms * 1e-3) / (torch.cuda.get_device_properties(device).multi_processor_count
+                                               * 128 * clocks.get("sm_max_mhz", 1965.0) * 1e6
+                                               if clocks.get("sm_max_mhz") else 148 * 128 * 1.965e9),
+                     "hbm_bound_case": {"queries": n_lr, "probes": p_used, "kernel_ms": lr_avg_ms,
+                                        "algorithmic_bytes_per_launch": lr_bytes,
+                                        "achieved": lr_bytes / (lr_avg_ms * 1e-3) / 1e9,
+                                        "frac": lr_bytes / (lr_avg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                        "note": "same kernel, so few queries that no bucket tile is shared"}},
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -202,4 +202,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
+// 2-D TMA tensor copy global -> shared (SASS UTMALDG): box at (c0 = column, c1 = row) of the
+// tensor described by `tmap`, completion counted in bytes on `bar`.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
 #endif  // __CUDACC__

@@ -9,15 +9,19 @@
 // probes it):
 //   plan_count / plan_scan / plan_scatter : (query, probe) pairs grouped by bucket
 //   item = (bucket, row chunk, group of <= kG queries of that bucket)
-//   scan kernel: persistent CTAs pull items from an atomic counter.  One producer warp
-//     streams the chunk's rows HBM -> shared memory with 1-D bulk-async copies (TMA,
-//     SASS UBLKCP) into a ring of stages guarded by full/empty mbarriers; four consumer
-//     warps (one row per thread, padded row stride => conflict-free 128-bit LDS, query
-//     values broadcast) accumulate the distances of the row to the item's queries and
+//   scan kernel: persistent CTAs pull items from an atomic counter.  One elected producer
+//     thread streams the chunk's rows HBM/L2 -> shared memory with 2-D TMA tensor copies
+//     (cp.async.bulk.tensor, SASS UTMALDG; box = 128 rows x 32 floats, SWIZZLE_128B) into a
+//     ring of stages guarded by full/empty mbarriers; four consumer warps (one row per
+//     thread; the hardware swizzle makes the 128-bit row reads conflict-free while the query
+//     values are broadcast) accumulate the distances of the row to the item's queries and
 //     keep one register-resident sorted top-k list per (warp, query).
 //   merge kernel: one warp per query merges its partial lists -> ids/dists/n_candidates.
 // All top-k decisions use the (distance, id) lexicographic order, so the result does not
 // depend on item scheduling or on how many GPUs the database is sharded over.
+#include <cuda.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -25,7 +29,9 @@ namespace {
 constexpr int kConsumerWarps = 4;
 constexpr int kTileRows = 32 * kConsumerWarps;  // rows per stage
 constexpr int kG = 8;                           // queries per item
-constexpr int kChunkFloats = 64;                // columns per stage (256 B per row copy)
+constexpr int kBoxCols = 32;                    // TMA box: 32 floats = one 128-byte swizzle row
+constexpr int kBoxFloats = kTileRows * kBoxCols;  // 16 KB per box
+constexpr int kBoxesPerStage = 2;               // a stage holds 64 columns of 128 rows (32 KB)
 constexpr int kMaxChunksPerBucket = 64;
 constexpr int kCtasPerSm = 2;
 constexpr size_t kSmemBudget = 112 * 1024;  // per CTA, leaves room for 2 CTAs / SM
@@ -33,11 +39,9 @@ constexpr size_t kSmemBudget = 112 * 1024;  // per CTA, leaves room for 2 CTAs /
 struct ScanGeom {
   int d;         // real columns
   int d_pad;     // row stride of x_sorted (multiple of 4)
-  int dc;        // columns per stage chunk (multiple of 4)
-  int n_chunks;  // ceil(d_pad / dc)
-  int stride_f;  // smem row stride in floats: (stride_f / 4) is odd => conflict-free LDS.128
+  int n_boxes;   // ceil(d_pad / 32) column boxes per row tile
+  int n_chunks;  // ceil(n_boxes / kBoxesPerStage) stages per row tile
   int stages;
-  size_t stage_floats;
   size_t smem_bytes;
 };
 
@@ -45,18 +49,17 @@ ScanGeom scan_geom(int d, bool async) {
   ScanGeom g;
   g.d = d;
   g.d_pad = (d + 3) / 4 * 4;
-  g.dc = g.d_pad < kChunkFloats ? g.d_pad : kChunkFloats;
-  g.n_chunks = (g.d_pad + g.dc - 1) / g.dc;
-  g.stride_f = ((g.dc / 4) % 2 == 0) ? g.dc + 4 : g.dc;
-  g.stage_floats = (size_t)kTileRows * g.stride_f;
+  g.n_boxes = (g.d_pad + kBoxCols - 1) / kBoxCols;
+  g.n_chunks = (g.n_boxes + kBoxesPerStage - 1) / kBoxesPerStage;
+  const size_t stage_bytes = (size_t)kBoxesPerStage * kBoxFloats * sizeof(float);
   const size_t q_bytes = (size_t)kG * g.d_pad * sizeof(float);
-  const size_t fixed = q_bytes + 256;
+  const size_t fixed = q_bytes + 256 + 1024;  // + barriers/item slots + 1024-byte alignment slack
   g.stages = 1;
   if (async) {
     g.stages = 4;
-    while (g.stages > 2 && fixed + g.stages * g.stage_floats * sizeof(float) > kSmemBudget) --g.stages;
+    while (g.stages > 2 && fixed + g.stages * stage_bytes > kSmemBudget) --g.stages;
   }
-  g.smem_bytes = fixed + g.stages * g.stage_floats * sizeof(float);
+  g.smem_bytes = fixed + g.stages * stage_bytes;
   return g;
 }
 
@@ -112,21 +115,21 @@ struct ScanArgs {
   int dense_qgroups;
   int dense_items;
   int exclude_self;
-  int d, d_pad, dc, n_chunks, stride_f, stages;
+  int d, d_pad, n_boxes, n_chunks, stages;
 };
 
-// ---- per-chunk distance accumulation ----------------------------------------------------
-// xrow: this thread's row inside the stage (stride-padded), qs: query values of this chunk
-// (query g at qs + g * d_pad), nvec full float4 columns, tail = extra valid columns (0..3).
+// ---- per-box distance accumulation --------------------------------------------------------
+// xrow: this thread's 128-byte row inside a box whose 16-byte chunks are XOR-swizzled with
+// (row & 7) (TMA SWIZZLE_128B); xr = row & 7; qs: query values of the box's first column
+// (query g at qs + g * d_pad); nvec full float4 columns, tail = extra valid columns (0..3).
 template <int METRIC, int NG>
-__device__ __forceinline__ void consume_chunk(float (&acc)[kG], float& xx,
-                                              const float* __restrict__ xrow,
-                                              const float* __restrict__ qs, int d_pad, int nvec,
-                                              int tail) {
-  const float4* x4 = reinterpret_cast<const float4*>(xrow);
+__device__ __forceinline__ void consume_box(float (&acc)[kG], float& xx,
+                                            const float* __restrict__ xrow, int xr,
+                                            const float* __restrict__ qs, int d_pad, int nvec,
+                                            int tail) {
 #pragma unroll 4
   for (int v = 0; v < nvec; ++v) {
-    const float4 xv = x4[v];
+    const float4 xv = *reinterpret_cast<const float4*>(xrow + ((v ^ xr) << 2));
     if (METRIC == NLSH_METRIC_ANGULAR || METRIC == NLSH_METRIC_COSINE) {
       xx = fmaf(xv.x, xv.x, xx);
       xx = fmaf(xv.y, xv.y, xx);
@@ -159,7 +162,7 @@ __device__ __forceinline__ void consume_chunk(float (&acc)[kG], float& xx,
   }
   // partial last vector (d not a multiple of 4): only the first `tail` components exist
   for (int c = 0; c < tail; ++c) {
-    const float xv = xrow[4 * nvec + c];
+    const float xv = xrow[((nvec ^ xr) << 2) + c];
     if (METRIC == NLSH_METRIC_ANGULAR || METRIC == NLSH_METRIC_COSINE) xx = fmaf(xv, xv, xx);
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
@@ -179,16 +182,16 @@ __device__ __forceinline__ void consume_chunk(float (&acc)[kG], float& xx,
 
 template <int METRIC>
 __device__ __forceinline__ void consume_dispatch(int ng, float (&acc)[kG], float& xx,
-                                                 const float* xrow, const float* qs, int d_pad,
-                                                 int nvec, int tail) {
+                                                 const float* xrow, int xr, const float* qs,
+                                                 int d_pad, int nvec, int tail) {
   if (ng <= 1)
-    consume_chunk<METRIC, 1>(acc, xx, xrow, qs, d_pad, nvec, tail);
+    consume_box<METRIC, 1>(acc, xx, xrow, xr, qs, d_pad, nvec, tail);
   else if (ng <= 2)
-    consume_chunk<METRIC, 2>(acc, xx, xrow, qs, d_pad, nvec, tail);
+    consume_box<METRIC, 2>(acc, xx, xrow, xr, qs, d_pad, nvec, tail);
   else if (ng <= 4)
-    consume_chunk<METRIC, 4>(acc, xx, xrow, qs, d_pad, nvec, tail);
+    consume_box<METRIC, 4>(acc, xx, xrow, xr, qs, d_pad, nvec, tail);
   else
-    consume_chunk<METRIC, 8>(acc, xx, xrow, qs, d_pad, nvec, tail);
+    consume_box<METRIC, 8>(acc, xx, xrow, xr, qs, d_pad, nvec, tail);
 }
 
 template <int METRIC>
@@ -197,6 +200,17 @@ __device__ __forceinline__ float finalize_distance(float acc, float xx) {
   if (METRIC == NLSH_METRIC_L2SQ) return acc;
   if (METRIC == NLSH_METRIC_ANGULAR) return 1.0f - acc / fmaxf(sqrtf(xx), 1e-8f);
   return 1.0f - acc / sqrtf(xx);  // precompute._cosine_distance: no clamp
+}
+
+// Rows of a bucket (or of the dense row range) are split into nch balanced chunks whose
+// length is a multiple of the row tile: chunk c covers [c * rc, min(size, (c + 1) * rc)).
+__host__ __device__ __forceinline__ int chunk_count(int size, int rchunk, int max_chunks) {
+  int nch = (size + rchunk - 1) / rchunk;
+  return nch > max_chunks ? max_chunks : nch;
+}
+__host__ __device__ __forceinline__ int chunk_rows(int size, int nch) {
+  const int per = (size + nch - 1) / nch;
+  return (per + kTileRows - 1) / kTileRows * kTileRows;
 }
 
 struct Item {
@@ -235,10 +249,13 @@ __device__ __forceinline__ Item decode_item(const ScanArgs& a, int item) {
   const int gq = local - c * ngroups;
   const int r0 = a.offsets[b];
   const int size = a.offsets[b + 1] - r0;
-  int nch = (size + a.rchunk - 1) / a.rchunk;
-  if (nch > a.max_chunks) nch = a.max_chunks;
-  it.row0 = (long long)r0 + (long long)c * a.rchunk;
-  it.row1 = (c == nch - 1) ? (long long)r0 + size : it.row0 + a.rchunk;
+  const int nch = chunk_count(size, a.rchunk, a.max_chunks);
+  const int rc = chunk_rows(size, nch);
+  long long lo = (long long)c * rc, hi = lo + rc;
+  if (lo > size) lo = size;
+  if (hi > size || c == nch - 1) hi = size;
+  it.row0 = r0 + lo;
+  it.row1 = r0 + hi;
   it.chunk = c;
   it.pair_base = p0 + gq * kG;
   const int left = nq - gq * kG;
@@ -246,14 +263,18 @@ __device__ __forceinline__ Item decode_item(const ScanArgs& a, int item) {
   return it;
 }
 
-// Scan kernel.  ASYNC: warps 0..3 consume, warp 4 produces with bulk-async copies.
-// !ASYNC (debug / A-B): 4 warps stage each chunk cooperatively with plain loads.
+// Scan kernel.  ASYNC: warps 0..3 consume, one elected thread of warp 4 produces with 2-D
+// TMA tensor copies.  !ASYNC (debug / A-B): 4 warps stage each chunk cooperatively with plain
+// loads into the same swizzled layout.
 template <int METRIC, int KPL, bool ASYNC>
 __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kConsumerWarps, kCtasPerSm)
-    scan_kernel(const ScanArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* stage_buf = reinterpret_cast<float*>(smem_raw);
-  float* qs = stage_buf + (size_t)a.stages * kTileRows * a.stride_f;
+    scan_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ unsigned char smem_raw[];
+  // SWIZZLE_128B boxes need 1024-byte aligned shared addresses
+  unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* stage_buf = reinterpret_cast<float*>(smem_al);
+  constexpr size_t stage_floats = (size_t)kBoxesPerStage * kBoxFloats;
+  float* qs = stage_buf + (size_t)a.stages * stage_floats;
   unsigned char* tail_ptr = reinterpret_cast<unsigned char*>(qs + (size_t)kG * a.d_pad);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail_ptr);  // [stages <= 4]
   uint64_t* empty_bar = full_bar + 4;                          // [stages <= 4]
@@ -263,7 +284,6 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const size_t stage_floats = (size_t)kTileRows * a.stride_f;
 
   if (ASYNC && tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
@@ -279,7 +299,6 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
   unsigned ring = 0;  // stage uses so far (same sequence in producer and consumers)
   int round = 0;
   int item = s_item[0];
-  const int tail_cols = a.d - (a.d_pad - 4);  // valid columns of the last float4 (1..4)
 
   while (item < total_items) {
     if (tid == 0) s_item[(round + 1) & 1] = atomicAdd(a.item_counter, 1);
@@ -317,9 +336,11 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
           if (g < it.ng) self_id[g] = (int)(a.self_offset + s_f[g]);
       }
 
-      const float* xrow_base = stage_buf + (size_t)(warp * 32 + lane) * a.stride_f;
+      const int r_local = warp * 32 + lane;
+      const int xr = r_local & 7;
       for (int t = 0; t < n_tiles; ++t) {
-        const long long row = it.row0 + (long long)t * kTileRows + warp * 32 + lane;
+        const long long tile_row0 = it.row0 + (long long)t * kTileRows;
+        const long long row = tile_row0 + r_local;
         const bool valid = row < it.row1;
         int cand_id = NLSH_ID_SENTINEL;
         if (valid) cand_id = a.ids ? a.ids[row] : (int)row;  // latency hidden behind the chunk loop
@@ -327,33 +348,37 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
 #pragma unroll
         for (int g = 0; g < kG; ++g) acc[g] = 0.f;
         float xx = 0.f;
-        const long long tile_row0 = it.row0 + (long long)t * kTileRows;
-        const int rows_in_tile =
-            (int)((it.row1 - tile_row0) < kTileRows ? (it.row1 - tile_row0) : kTileRows);
         for (int ch = 0; ch < a.n_chunks; ++ch) {
-          const int col0 = ch * a.dc;
-          const int cols = (a.d_pad - col0) < a.dc ? (a.d_pad - col0) : a.dc;
-          int nvec = cols >> 2;
-          int tail = 0;
-          if (ch == a.n_chunks - 1 && tail_cols < 4) {
-            nvec -= 1;
-            tail = tail_cols;
-          }
+          const int box0 = ch * kBoxesPerStage;
+          const int nb = (a.n_boxes - box0) < kBoxesPerStage ? (a.n_boxes - box0) : kBoxesPerStage;
           const int s = ASYNC ? (int)(ring % (unsigned)a.stages) : 0;
+          float* stage = stage_buf + s * stage_floats;
           if (ASYNC) {
             mbar_wait(&full_bar[s], (ring / (unsigned)a.stages) & 1u);
           } else {
+            // same layout as the TMA boxes: box-major, 128-byte rows, chunk ^= (row & 7)
+            const int rows_in_tile =
+                (int)((it.row1 - tile_row0) < kTileRows ? (it.row1 - tile_row0) : kTileRows);
+            const int cols = (a.d_pad - box0 * kBoxCols) < nb * kBoxCols ? (a.d_pad - box0 * kBoxCols)
+                                                                       : nb * kBoxCols;
             const int cvec = cols >> 2;
             for (int idx = tid; idx < rows_in_tile * cvec; idx += 32 * kConsumerWarps) {
               const int r = idx / cvec, v = idx - r * cvec;
               const float4 val = __ldcs(reinterpret_cast<const float4*>(
-                                            a.xs + (size_t)(tile_row0 + r) * a.d_pad + col0) + v);
-              *reinterpret_cast<float4*>(stage_buf + (size_t)r * a.stride_f + 4 * v) = val;
+                                            a.xs + (size_t)(tile_row0 + r) * a.d_pad + box0 * kBoxCols) + v);
+              const int b = v >> 3, c = v & 7;
+              *reinterpret_cast<float4*>(stage + b * kBoxFloats + r * kBoxCols + ((c ^ (r & 7)) << 2)) = val;
             }
             __syncthreads();
           }
-          consume_dispatch<METRIC>(it.ng, acc, xx, xrow_base + s * stage_floats, qs + col0, a.d_pad,
-                                   nvec, tail);
+          for (int b = 0; b < nb; ++b) {
+            const int col0 = (box0 + b) * kBoxCols;
+            int cols = a.d - col0;  // valid (unpadded) columns of this box
+            if (cols > kBoxCols) cols = kBoxCols;
+            if (cols <= 0) break;
+            consume_dispatch<METRIC>(it.ng, acc, xx, stage + b * kBoxFloats + r_local * kBoxCols, xr,
+                                     qs + col0, a.d_pad, cols >> 2, cols & 3);
+          }
           if (ASYNC) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -387,26 +412,25 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
         }
       }
     } else if (ASYNC) {
-      // ---- producer warp: stream the item's rows, chunk by chunk ----------------------
-      for (int t = 0; t < n_tiles; ++t) {
-        const long long tile_row0 = it.row0 + (long long)t * kTileRows;
-        const int rows_in_tile =
-            (int)((it.row1 - tile_row0) < kTileRows ? (it.row1 - tile_row0) : kTileRows);
-        for (int ch = 0; ch < a.n_chunks; ++ch) {
-          const int col0 = ch * a.dc;
-          const int cols = (a.d_pad - col0) < a.dc ? (a.d_pad - col0) : a.dc;
-          const unsigned bytes = (unsigned)cols * 4u;
-          const int s = (int)(ring % (unsigned)a.stages);
-          mbar_wait(&empty_bar[s], ((ring / (unsigned)a.stages) & 1u) ^ 1u);
-          if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], bytes * (unsigned)rows_in_tile);
-          __syncwarp();
-          float* dst = stage_buf + s * stage_floats;
-          const float* src = a.xs + (size_t)tile_row0 * a.d_pad + col0;
-          for (int r = lane; r < rows_in_tile; r += 32)
-            bulk_g2s(dst + (size_t)r * a.stride_f, src + (size_t)r * a.d_pad, bytes, &full_bar[s]);
-          ++ring;
+      // ---- producer: one elected thread streams the item's row tiles, stage by stage -----
+      if (lane == 0) {
+        for (int t = 0; t < n_tiles; ++t) {
+          const int tile_row0 = (int)(it.row0 + (long long)t * kTileRows);
+          for (int ch = 0; ch < a.n_chunks; ++ch) {
+            const int box0 = ch * kBoxesPerStage;
+            const int nb = (a.n_boxes - box0) < kBoxesPerStage ? (a.n_boxes - box0) : kBoxesPerStage;
+            const int s = (int)(ring % (unsigned)a.stages);
+            mbar_wait(&empty_bar[s], ((ring / (unsigned)a.stages) & 1u) ^ 1u);
+            // a box is always written in full (rows / columns past the tensor are zero filled)
+            mbar_arrive_expect_tx(&full_bar[s], (unsigned)(nb * kBoxFloats * sizeof(float)));
+            float* dst = stage_buf + s * stage_floats;
+            for (int b = 0; b < nb; ++b)
+              tma_load_2d(dst + b * kBoxFloats, &tmap, (box0 + b) * kBoxCols, tile_row0, &full_bar[s]);
+            ++ring;
+          }
         }
       }
+      __syncwarp();
     }
     __syncthreads();
     ++round;
@@ -449,9 +473,7 @@ __global__ void __launch_bounds__(1024)
     if (b < n_buckets) {
       c = cnt[b];
       const int size = offsets[b + 1] - offsets[b];
-      int nch = (size + rchunk - 1) / rchunk;
-      if (nch > max_chunks) nch = max_chunks;
-      items = ((c + kG - 1) / kG) * nch;
+      items = ((c + kG - 1) / kG) * chunk_count(size, rchunk, max_chunks);
     }
     int ic = c, ii = items;
 #pragma unroll
@@ -559,8 +581,7 @@ __global__ void __launch_bounds__(128)
       if (!probe_valid(probes, offsets, n_buckets, p, f, b)) continue;
       const int size = offsets[b + 1] - offsets[b];
       ncand += size;
-      nch = (size + rchunk - 1) / rchunk;
-      if (nch > max_chunks) nch = max_chunks;
+      nch = chunk_count(size, rchunk, max_chunks);
     }
     for (int c = 0; c < nch; ++c) {
       for (int w = 0; w < kConsumerWarps; ++w) {
@@ -652,35 +673,78 @@ __global__ void recall_hits_kernel(const long long* __restrict__ gt, int k_gt,
 
 // ---- launch helpers ------------------------------------------------------------------------
 template <int METRIC, int KPL>
-int launch_scan(const ScanArgs& a, const ScanGeom& g, bool async, int grid, cudaStream_t st) {
+int launch_scan(const ScanArgs& a, const CUtensorMap& tmap, const ScanGeom& g, bool async, int grid,
+                cudaStream_t st) {
   if (async) {
     auto kern = scan_kernel<METRIC, KPL, true>;
     NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)g.smem_bytes));
-    kern<<<grid, 32 * (kConsumerWarps + 1), g.smem_bytes, st>>>(a);
+    kern<<<grid, 32 * (kConsumerWarps + 1), g.smem_bytes, st>>>(a, tmap);
   } else {
     auto kern = scan_kernel<METRIC, KPL, false>;
     NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)g.smem_bytes));
-    kern<<<grid, 32 * kConsumerWarps, g.smem_bytes, st>>>(a);
+    kern<<<grid, 32 * kConsumerWarps, g.smem_bytes, st>>>(a, tmap);
   }
   return nlsh_check_cuda(nlsh_post_launch(), "scan_kernel launch");
 }
 
 template <int METRIC>
-int launch_scan_k(const ScanArgs& a, const ScanGeom& g, bool async, int grid, cudaStream_t st) {
-  if (a.k <= 32) return launch_scan<METRIC, 1>(a, g, async, grid, st);
-  if (a.k <= 64) return launch_scan<METRIC, 2>(a, g, async, grid, st);
-  return launch_scan<METRIC, 4>(a, g, async, grid, st);
+int launch_scan_k(const ScanArgs& a, const CUtensorMap& tmap, const ScanGeom& g, bool async, int grid,
+                  cudaStream_t st) {
+  if (a.k <= 32) return launch_scan<METRIC, 1>(a, tmap, g, async, grid, st);
+  if (a.k <= 64) return launch_scan<METRIC, 2>(a, tmap, g, async, grid, st);
+  return launch_scan<METRIC, 4>(a, tmap, g, async, grid, st);
+}
+
+// The 2-D tensor map of the row-major [n_rows, d_pad] fp32 matrix the scan streams:
+// box = kBoxCols floats (128 bytes) x kTileRows rows, SWIZZLE_128B, zero fill out of bounds.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_row_tensor_map(CUtensorMap* tmap, const float* base, long long n_rows, int d_pad) {
+  static EncodeTiledFn encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    NLSH_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      nlsh_set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return NLSH_ERR_CUDA;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)(n_rows > 0 ? n_rows : 1)};
+  const cuuint64_t strides[1] = {(cuuint64_t)d_pad * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kBoxCols, (cuuint32_t)kTileRows};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims,
+                            strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    nlsh_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld, d_pad=%d)", (int)r,
+                   n_rows, d_pad);
+    return NLSH_ERR_CUDA;
+  }
+  return NLSH_OK;
 }
 
 int launch_scan_metric(int metric, const ScanArgs& a, const ScanGeom& g, bool async, int grid,
                        cudaStream_t st) {
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (async) {
+    const int rc = make_row_tensor_map(&tmap, a.xs, a.n_rows, a.d_pad);
+    if (rc != NLSH_OK) return rc;
+  }
   switch (metric) {
-    case NLSH_METRIC_L2: return launch_scan_k<NLSH_METRIC_L2>(a, g, async, grid, st);
-    case NLSH_METRIC_ANGULAR: return launch_scan_k<NLSH_METRIC_ANGULAR>(a, g, async, grid, st);
-    case NLSH_METRIC_L2SQ: return launch_scan_k<NLSH_METRIC_L2SQ>(a, g, async, grid, st);
-    default: return launch_scan_k<NLSH_METRIC_COSINE>(a, g, async, grid, st);
+    case NLSH_METRIC_L2: return launch_scan_k<NLSH_METRIC_L2>(a, tmap, g, async, grid, st);
+    case NLSH_METRIC_ANGULAR: return launch_scan_k<NLSH_METRIC_ANGULAR>(a, tmap, g, async, grid, st);
+    case NLSH_METRIC_L2SQ: return launch_scan_k<NLSH_METRIC_L2SQ>(a, tmap, g, async, grid, st);
+    default: return launch_scan_k<NLSH_METRIC_COSINE>(a, tmap, g, async, grid, st);
   }
 }
 
@@ -850,9 +914,8 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   a.exclude_self = 0;
   a.d = geom.d;
   a.d_pad = geom.d_pad;
-  a.dc = geom.dc;
+  a.n_boxes = geom.n_boxes;
   a.n_chunks = geom.n_chunks;
-  a.stride_f = geom.stride_f;
   a.stages = geom.stages;
   const int grid = nlsh_num_sms() * kCtasPerSm;
   nlsh_profile_mark(st, true);
@@ -938,9 +1001,8 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
   a.exclude_self = exclude_self ? 1 : 0;
   a.d = geom.d;
   a.d_pad = geom.d_pad;
-  a.dc = geom.dc;
+  a.n_boxes = geom.n_boxes;
   a.n_chunks = geom.n_chunks;
-  a.stride_f = geom.stride_f;
   a.stages = geom.stages;
   const int grid = nlsh_num_sms() * kCtasPerSm;
   if (n_rows > 0) {
