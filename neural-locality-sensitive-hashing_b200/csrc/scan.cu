@@ -251,11 +251,11 @@ __device__ __forceinline__ Item decode_item(const ScanArgs& a, int item) {
   const int size = a.offsets[b + 1] - r0;
   const int nch = chunk_count(size, a.rchunk, a.max_chunks);
   const int rc = chunk_rows(size, nch);
-  long long lo = (long long)c * rc, hi = lo + rc;
-  if (lo > size) lo = size;
-  if (hi > size || c == nch - 1) hi = size;
-  it.row0 = r0 + lo;
-  it.row1 = r0 + hi;
+  long long c_lo = (long long)c * rc, c_hi = c_lo + rc;
+  if (c_lo > size) c_lo = size;
+  if (c_hi > size || c == nch - 1) c_hi = size;
+  it.row0 = r0 + c_lo;
+  it.row1 = r0 + c_hi;
   it.chunk = c;
   it.pair_base = p0 + gq * kG;
   const int left = nq - gq * kG;
