@@ -176,10 +176,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware
       : "memory");
   return ok != 0;
 }
@@ -188,7 +188,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // completes traps (-> CUDA error on the host) instead of hanging the device.
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls > (1u << 24)) __trap();
+    if (++polls > (1u << 22)) __trap();
   }
 }
 // global -> shared bulk copy (SASS UBLKCP), completion counted in bytes on `bar`.

@@ -122,76 +122,89 @@ struct ScanArgs {
 // xrow: this thread's 128-byte row inside a box whose 16-byte chunks are XOR-swizzled with
 // (row & 7) (TMA SWIZZLE_128B); xr = row & 7; qs: query values of the box's first column
 // (query g at qs + g * d_pad); nvec full float4 columns, tail = extra valid columns (0..3).
+// Accumulators are packed float2 pairs so the arithmetic issues as Blackwell's two-wide fp32
+// instructions (FADD2 / FFMA2): acc[g][0] sums columns 0,1 (mod 4), acc[g][1] columns 2,3.
+struct Acc {
+  float2 a[kG][2];
+  float2 xx[2];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int g = 0; g < kG; ++g) a[g][0] = a[g][1] = make_float2(0.f, 0.f);
+    xx[0] = xx[1] = make_float2(0.f, 0.f);
+  }
+  __device__ __forceinline__ float sum(int g) const {
+    return (a[g][0].x + a[g][0].y) + (a[g][1].x + a[g][1].y);
+  }
+  __device__ __forceinline__ float sum_xx() const { return (xx[0].x + xx[0].y) + (xx[1].x + xx[1].y); }
+};
+
 template <int METRIC, int NG>
-__device__ __forceinline__ void consume_box(float (&acc)[kG], float& xx,
-                                            const float* __restrict__ xrow, int xr,
+__device__ __forceinline__ void consume_box(Acc& acc, const float* __restrict__ xrow, int xr,
                                             const float* __restrict__ qs, int d_pad, int nvec,
                                             int tail) {
-#pragma unroll 4
+  const float2 eps2 = make_float2(1e-6f, 1e-6f);
+#pragma unroll 8
   for (int v = 0; v < nvec; ++v) {
     const float4 xv = *reinterpret_cast<const float4*>(xrow + ((v ^ xr) << 2));
+    const float2 x01 = make_float2(xv.x, xv.y), x23 = make_float2(xv.z, xv.w);
+    const float2 n01 = make_float2(-xv.x, -xv.y), n23 = make_float2(-xv.z, -xv.w);
     if (METRIC == NLSH_METRIC_ANGULAR || METRIC == NLSH_METRIC_COSINE) {
-      xx = fmaf(xv.x, xv.x, xx);
-      xx = fmaf(xv.y, xv.y, xx);
-      xx = fmaf(xv.z, xv.z, xx);
-      xx = fmaf(xv.w, xv.w, xx);
+      acc.xx[0] = __ffma2_rn(x01, x01, acc.xx[0]);
+      acc.xx[1] = __ffma2_rn(x23, x23, acc.xx[1]);
     }
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       const float4 qv = *reinterpret_cast<const float4*>(qs + g * d_pad + 4 * v);
+      const float2 q01 = make_float2(qv.x, qv.y), q23 = make_float2(qv.z, qv.w);
       if (METRIC == NLSH_METRIC_L2) {
         // F.pairwise_distance: (q - x) + eps, squared and summed (nlsh/data.py:201)
-        float t;
-        t = __fadd_rn(__fsub_rn(qv.x, xv.x), 1e-6f); acc[g] = fmaf(t, t, acc[g]);
-        t = __fadd_rn(__fsub_rn(qv.y, xv.y), 1e-6f); acc[g] = fmaf(t, t, acc[g]);
-        t = __fadd_rn(__fsub_rn(qv.z, xv.z), 1e-6f); acc[g] = fmaf(t, t, acc[g]);
-        t = __fadd_rn(__fsub_rn(qv.w, xv.w), 1e-6f); acc[g] = fmaf(t, t, acc[g]);
+        const float2 t01 = __fadd2_rn(__fadd2_rn(q01, n01), eps2);
+        const float2 t23 = __fadd2_rn(__fadd2_rn(q23, n23), eps2);
+        acc.a[g][0] = __ffma2_rn(t01, t01, acc.a[g][0]);
+        acc.a[g][1] = __ffma2_rn(t23, t23, acc.a[g][1]);
       } else if (METRIC == NLSH_METRIC_L2SQ) {
-        float t;
-        t = qv.x - xv.x; acc[g] = fmaf(t, t, acc[g]);
-        t = qv.y - xv.y; acc[g] = fmaf(t, t, acc[g]);
-        t = qv.z - xv.z; acc[g] = fmaf(t, t, acc[g]);
-        t = qv.w - xv.w; acc[g] = fmaf(t, t, acc[g]);
+        const float2 t01 = __fadd2_rn(q01, n01);
+        const float2 t23 = __fadd2_rn(q23, n23);
+        acc.a[g][0] = __ffma2_rn(t01, t01, acc.a[g][0]);
+        acc.a[g][1] = __ffma2_rn(t23, t23, acc.a[g][1]);
       } else {
-        acc[g] = fmaf(qv.x, xv.x, acc[g]);
-        acc[g] = fmaf(qv.y, xv.y, acc[g]);
-        acc[g] = fmaf(qv.z, xv.z, acc[g]);
-        acc[g] = fmaf(qv.w, xv.w, acc[g]);
+        acc.a[g][0] = __ffma2_rn(q01, x01, acc.a[g][0]);
+        acc.a[g][1] = __ffma2_rn(q23, x23, acc.a[g][1]);
       }
     }
   }
   // partial last vector (d not a multiple of 4): only the first `tail` components exist
   for (int c = 0; c < tail; ++c) {
     const float xv = xrow[((nvec ^ xr) << 2) + c];
-    if (METRIC == NLSH_METRIC_ANGULAR || METRIC == NLSH_METRIC_COSINE) xx = fmaf(xv, xv, xx);
+    if (METRIC == NLSH_METRIC_ANGULAR || METRIC == NLSH_METRIC_COSINE)
+      acc.xx[0].x = fmaf(xv, xv, acc.xx[0].x);
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       const float qv = qs[g * d_pad + 4 * nvec + c];
       if (METRIC == NLSH_METRIC_L2) {
         const float t = __fadd_rn(__fsub_rn(qv, xv), 1e-6f);
-        acc[g] = fmaf(t, t, acc[g]);
+        acc.a[g][0].x = fmaf(t, t, acc.a[g][0].x);
       } else if (METRIC == NLSH_METRIC_L2SQ) {
         const float t = qv - xv;
-        acc[g] = fmaf(t, t, acc[g]);
+        acc.a[g][0].x = fmaf(t, t, acc.a[g][0].x);
       } else {
-        acc[g] = fmaf(qv, xv, acc[g]);
+        acc.a[g][0].x = fmaf(qv, xv, acc.a[g][0].x);
       }
     }
   }
 }
 
 template <int METRIC>
-__device__ __forceinline__ void consume_dispatch(int ng, float (&acc)[kG], float& xx,
-                                                 const float* xrow, int xr, const float* qs,
-                                                 int d_pad, int nvec, int tail) {
+__device__ __forceinline__ void consume_dispatch(int ng, Acc& acc, const float* xrow, int xr,
+                                                 const float* qs, int d_pad, int nvec, int tail) {
   if (ng <= 1)
-    consume_box<METRIC, 1>(acc, xx, xrow, xr, qs, d_pad, nvec, tail);
+    consume_box<METRIC, 1>(acc, xrow, xr, qs, d_pad, nvec, tail);
   else if (ng <= 2)
-    consume_box<METRIC, 2>(acc, xx, xrow, xr, qs, d_pad, nvec, tail);
+    consume_box<METRIC, 2>(acc, xrow, xr, qs, d_pad, nvec, tail);
   else if (ng <= 4)
-    consume_box<METRIC, 4>(acc, xx, xrow, xr, qs, d_pad, nvec, tail);
+    consume_box<METRIC, 4>(acc, xrow, xr, qs, d_pad, nvec, tail);
   else
-    consume_box<METRIC, 8>(acc, xx, xrow, xr, qs, d_pad, nvec, tail);
+    consume_box<METRIC, 8>(acc, xrow, xr, qs, d_pad, nvec, tail);
 }
 
 template <int METRIC>
@@ -344,10 +357,8 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
         const bool valid = row < it.row1;
         int cand_id = NLSH_ID_SENTINEL;
         if (valid) cand_id = a.ids ? a.ids[row] : (int)row;  // latency hidden behind the chunk loop
-        float acc[kG];
-#pragma unroll
-        for (int g = 0; g < kG; ++g) acc[g] = 0.f;
-        float xx = 0.f;
+        Acc acc;
+        acc.clear();
         for (int ch = 0; ch < a.n_chunks; ++ch) {
           const int box0 = ch * kBoxesPerStage;
           const int nb = (a.n_boxes - box0) < kBoxesPerStage ? (a.n_boxes - box0) : kBoxesPerStage;
@@ -376,7 +387,7 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
             int cols = a.d - col0;  // valid (unpadded) columns of this box
             if (cols > kBoxCols) cols = kBoxCols;
             if (cols <= 0) break;
-            consume_dispatch<METRIC>(it.ng, acc, xx, stage + b * kBoxFloats + r_local * kBoxCols, xr,
+            consume_dispatch<METRIC>(it.ng, acc, stage + b * kBoxFloats + r_local * kBoxCols, xr,
                                      qs + col0, a.d_pad, cols >> 2, cols & 3);
           }
           if (ASYNC) {
@@ -387,10 +398,11 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
           }
           ++ring;
         }
+        const float xx = acc.sum_xx();
 #pragma unroll
         for (int g = 0; g < kG; ++g) {
           if (g < it.ng) {
-            const float dist = finalize_distance<METRIC>(acc[g], xx);
+            const float dist = finalize_distance<METRIC>(acc.sum(g), xx);
             top[g].offer(dist, cand_id, valid && cand_id != self_id[g], a.k);
           }
         }
