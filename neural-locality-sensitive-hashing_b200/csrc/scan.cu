@@ -14,9 +14,12 @@
 //     (cp.async.bulk.tensor, SASS UTMALDG; box = 128 rows x 32 floats, SWIZZLE_128B) into a
 //     ring of stages guarded by full/empty mbarriers; four consumer warps (one row per
 //     thread; the hardware swizzle makes the 128-bit row reads conflict-free while the query
-//     values are broadcast) accumulate the distances of the row to the item's queries and
-//     keep one register-resident sorted top-k list per (warp, query).
-//   merge kernel: one warp per query merges its partial lists -> ids/dists/n_candidates.
+//     values are broadcast) accumulate the distances of the row to the item's queries with
+//     packed fp32x2 math; per row tile the 128 x kG scores are exchanged through shared
+//     memory so that each warp owns the register-resident sorted top-k lists of two of the
+//     item's queries (threshold-filtered by ballot, so inserts are rare).
+//   merge kernel: one warp per query merges its partial lists -> ids/dists/n_candidates
+//     (for L2 the lists hold squared distances; the square root is taken once, here).
 // All top-k decisions use the (distance, id) lexicographic order, so the result does not
 // depend on item scheduling or on how many GPUs the database is sharded over.
 #include <cuda.h>
@@ -33,6 +36,8 @@ constexpr int kBoxCols = 32;                    // TMA box: 32 floats = one 128-
 constexpr int kBoxFloats = kTileRows * kBoxCols;  // 16 KB per box
 constexpr int kBoxesPerStage = 2;               // a stage holds 64 columns of 128 rows (32 KB)
 constexpr int kMaxChunksPerBucket = 64;
+constexpr int kListsPerWarp = kG / kConsumerWarps;  // queries whose top-k a warp owns
+constexpr size_t kExchangeBytes = 2 * (kG + 1) * kTileRows * sizeof(float);
 constexpr int kCtasPerSm = 2;
 constexpr size_t kSmemBudget = 112 * 1024;  // per CTA, leaves room for 2 CTAs / SM
 
@@ -53,7 +58,8 @@ ScanGeom scan_geom(int d, bool async) {
   g.n_chunks = (g.n_boxes + kBoxesPerStage - 1) / kBoxesPerStage;
   const size_t stage_bytes = (size_t)kBoxesPerStage * kBoxFloats * sizeof(float);
   const size_t q_bytes = (size_t)kG * g.d_pad * sizeof(float);
-  const size_t fixed = q_bytes + 256 + 1024;  // + barriers/item slots + 1024-byte alignment slack
+  // + score/id exchange (double buffered) + barriers/item slots + 1024-byte alignment slack
+  const size_t fixed = q_bytes + kExchangeBytes + 256 + 1024;
   g.stages = 1;
   if (async) {
     g.stages = 4;
@@ -207,9 +213,11 @@ __device__ __forceinline__ void consume_dispatch(int ng, Acc& acc, const float* 
     consume_box<METRIC, 8>(acc, xrow, xr, qs, d_pad, nvec, tail);
 }
 
+// Score kept in the top-k lists: the distance itself, except for L2 where it is the squared
+// distance (same order; merge_partials_kernel takes the root once per result).
 template <int METRIC>
 __device__ __forceinline__ float finalize_distance(float acc, float xx) {
-  if (METRIC == NLSH_METRIC_L2) return sqrtf(acc);
+  if (METRIC == NLSH_METRIC_L2) return acc;
   if (METRIC == NLSH_METRIC_L2SQ) return acc;
   if (METRIC == NLSH_METRIC_ANGULAR) return 1.0f - acc / fmaxf(sqrtf(xx), 1e-8f);
   return 1.0f - acc / sqrtf(xx);  // precompute._cosine_distance: no clamp
@@ -288,7 +296,9 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
   float* stage_buf = reinterpret_cast<float*>(smem_al);
   constexpr size_t stage_floats = (size_t)kBoxesPerStage * kBoxFloats;
   float* qs = stage_buf + (size_t)a.stages * stage_floats;
-  unsigned char* tail_ptr = reinterpret_cast<unsigned char*>(qs + (size_t)kG * a.d_pad);
+  float* score_s = qs + (size_t)kG * a.d_pad;                           // [2][kG][kTileRows]
+  int* id_s = reinterpret_cast<int*>(score_s + 2 * kG * kTileRows);     // [2][kTileRows]
+  unsigned char* tail_ptr = reinterpret_cast<unsigned char*>(id_s + 2 * kTileRows);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail_ptr);  // [stages <= 4]
   uint64_t* empty_bar = full_bar + 4;                          // [stages <= 4]
   int* s_f = reinterpret_cast<int*>(empty_bar + 4);            // [kG] flat probe index / query
@@ -337,16 +347,14 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory");
 
-      WarpTopK<KPL, int> top[kG];
+      // this warp owns the lists of queries g = warp + kConsumerWarps * i
+      WarpTopK<KPL, int> top[kListsPerWarp];
+      int self_id[kListsPerWarp];
 #pragma unroll
-      for (int g = 0; g < kG; ++g) top[g].init(NLSH_ID_SENTINEL);
-      int self_id[kG];
-#pragma unroll
-      for (int g = 0; g < kG; ++g) self_id[g] = -1;
-      if (a.exclude_self) {
-#pragma unroll
-        for (int g = 0; g < kG; ++g)
-          if (g < it.ng) self_id[g] = (int)(a.self_offset + s_f[g]);
+      for (int i = 0; i < kListsPerWarp; ++i) {
+        top[i].init(NLSH_ID_SENTINEL);
+        const int g = warp + kConsumerWarps * i;
+        self_id[i] = (a.exclude_self && g < it.ng) ? (int)(a.self_offset + s_f[g]) : -1;
       }
 
       const int r_local = warp * 32 + lane;
@@ -398,27 +406,41 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
           }
           ++ring;
         }
+        // ---- exchange: row-major scores -> the warp that owns each query's list ----------
+        // (double buffered on the tile parity: one named barrier per tile is enough)
+        float* sc = score_s + (t & 1) * (kG * kTileRows);
+        int* idb = id_s + (t & 1) * kTileRows;
         const float xx = acc.sum_xx();
+        idb[r_local] = valid ? cand_id : NLSH_ID_SENTINEL;
 #pragma unroll
-        for (int g = 0; g < kG; ++g) {
+        for (int g = 0; g < kG; ++g)
+          if (g < it.ng) sc[g * kTileRows + r_local] = finalize_distance<METRIC>(acc.sum(g), xx);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory");
+#pragma unroll
+        for (int i = 0; i < kListsPerWarp; ++i) {
+          const int g = warp + kConsumerWarps * i;
           if (g < it.ng) {
-            const float dist = finalize_distance<METRIC>(acc.sum(g), xx);
-            top[g].offer(dist, cand_id, valid && cand_id != self_id[g], a.k);
+#pragma unroll
+            for (int j = 0; j < kTileRows / 32; ++j) {
+              const int r = lane + 32 * j;
+              const int cid = idb[r];
+              top[i].offer(sc[g * kTileRows + r], cid, cid != NLSH_ID_SENTINEL && cid != self_id[i], a.k);
+            }
           }
         }
       }
-      // ---- partial lists: one per (query-probe, chunk, warp) ---------------------------
+      // ---- partial lists: one per (query-probe, chunk) ---------------------------------
 #pragma unroll
-      for (int g = 0; g < kG; ++g) {
+      for (int i = 0; i < kListsPerWarp; ++i) {
+        const int g = warp + kConsumerWarps * i;
         if (g < it.ng) {
-          const size_t slot =
-              ((size_t)s_f[g] * a.max_chunks + it.chunk) * kConsumerWarps + warp;
+          const size_t slot = (size_t)s_f[g] * a.max_chunks + it.chunk;
 #pragma unroll
           for (int j = 0; j < KPL; ++j) {
             const int pos = j * 32 + lane;
             if (pos < a.k) {
-              a.part_d[slot * a.k + pos] = top[g].d[j];
-              a.part_id[slot * a.k + pos] = top[g].id[j];
+              a.part_d[slot * a.k + pos] = top[i].d[j];
+              a.part_id[slot * a.k + pos] = top[i].id[j];
             }
           }
         }
@@ -572,7 +594,8 @@ __global__ void __launch_bounds__(128)
     merge_partials_kernel(const float* __restrict__ part_d, const int* __restrict__ part_id,
                           const int* __restrict__ probes, const int* __restrict__ offsets,
                           int n_buckets, int p, int k, int rchunk, int max_chunks, int dense,
-                          long long n_queries, long long id_offset, long long* __restrict__ ids_out,
+                          int sqrt_scores, long long n_queries, long long id_offset,
+                          long long* __restrict__ ids_out,
                           float* __restrict__ dists_out, int* __restrict__ ncand_out) {
   const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= n_queries) return;
@@ -596,18 +619,16 @@ __global__ void __launch_bounds__(128)
       nch = chunk_count(size, rchunk, max_chunks);
     }
     for (int c = 0; c < nch; ++c) {
-      for (int w = 0; w < kConsumerWarps; ++w) {
-        const size_t base = (((size_t)f * max_chunks + c) * kConsumerWarps + w) * k;
-        for (int e0 = 0; e0 < k; e0 += 32) {
-          const int e = e0 + lane;
-          float cd = 0.f;
-          int cid = NLSH_ID_SENTINEL;
-          if (e < k) {
-            cd = part_d[base + e];
-            cid = part_id[base + e];
-          }
-          top.offer(cd, cid, cid != NLSH_ID_SENTINEL, k);
+      const size_t base = ((size_t)f * max_chunks + c) * k;
+      for (int e0 = 0; e0 < k; e0 += 32) {
+        const int e = e0 + lane;
+        float cd = 0.f;
+        int cid = NLSH_ID_SENTINEL;
+        if (e < k) {
+          cd = part_d[base + e];
+          cid = part_id[base + e];
         }
+        top.offer(cd, cid, cid != NLSH_ID_SENTINEL, k);
       }
     }
   }
@@ -617,7 +638,7 @@ __global__ void __launch_bounds__(128)
     if (pos < k) {
       const int id = top.id[j];
       ids_out[q * k + pos] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
-      dists_out[q * k + pos] = top.d[j];
+      dists_out[q * k + pos] = sqrt_scores ? sqrtf(top.d[j]) : top.d[j];
     }
   }
   if (lane == 0 && ncand_out) ncand_out[q] = ncand;
@@ -762,22 +783,23 @@ int launch_scan_metric(int metric, const ScanArgs& a, const ScanGeom& g, bool as
 
 int launch_merge_partials(const float* part_d, const int* part_id, const int* probes,
                           const int* offsets, int n_buckets, int p, int k, int rchunk,
-                          int max_chunks, int dense, int64_t n_queries, int64_t id_offset,
+                          int max_chunks, int dense, int sqrt_scores, int64_t n_queries,
+                          int64_t id_offset,
                           int64_t* ids_out, float* dists_out, int* ncand_out, cudaStream_t st) {
   const unsigned blocks = (unsigned)((n_queries + 3) / 4);
   long long* ids_ll = reinterpret_cast<long long*>(ids_out);
   if (k <= 32)
     merge_partials_kernel<1><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
-                                                     k, rchunk, max_chunks, dense, n_queries,
-                                                     id_offset, ids_ll, dists_out, ncand_out);
+                                                     k, rchunk, max_chunks, dense, sqrt_scores,
+                                                     n_queries, id_offset, ids_ll, dists_out, ncand_out);
   else if (k <= 64)
     merge_partials_kernel<2><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
-                                                     k, rchunk, max_chunks, dense, n_queries,
-                                                     id_offset, ids_ll, dists_out, ncand_out);
+                                                     k, rchunk, max_chunks, dense, sqrt_scores,
+                                                     n_queries, id_offset, ids_ll, dists_out, ncand_out);
   else
     merge_partials_kernel<4><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
-                                                     k, rchunk, max_chunks, dense, n_queries,
-                                                     id_offset, ids_ll, dists_out, ncand_out);
+                                                     k, rchunk, max_chunks, dense, sqrt_scores,
+                                                     n_queries, id_offset, ids_ll, dists_out, ncand_out);
   return nlsh_check_cuda(nlsh_post_launch(), "merge_partials_kernel launch");
 }
 
@@ -808,7 +830,7 @@ QueryWorkspace carve_query_ws(void* base, int64_t nq, int p, int k, int d, int n
   w.item_off = ws.take<int>((size_t)n_buckets + 1);
   w.pairs = ws.take<int>((size_t)nq * p);
   w.qn = ws.take<float>((size_t)nq * d);
-  const size_t lists = (size_t)nq * p * max_chunks * kConsumerWarps * k;
+  const size_t lists = (size_t)nq * p * max_chunks * k;
   w.part_d = ws.take<float>(lists);
   w.part_id = ws.take<int>(lists);
   w.total = ws.total();
@@ -935,8 +957,8 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   nlsh_profile_mark(st, false);
   if (rc != NLSH_OK) return rc;
   return launch_merge_partials(w.part_d, w.part_id, probes, offsets, n_buckets, p, k, pol.rchunk,
-                               pol.max_chunks, 0, n_queries, id_offset, ids_out, dists_out,
-                               ncand_out, st);
+                               pol.max_chunks, 0, metric == NLSH_METRIC_L2 ? 1 : 0, n_queries,
+                               id_offset, ids_out, dists_out, ncand_out, st);
 }
 
 extern "C" size_t nlsh_knn_workspace_bytes(int64_t n_queries, int64_t n_rows, int32_t d, int32_t k) {
@@ -945,7 +967,7 @@ extern "C" size_t nlsh_knn_workspace_bytes(int64_t n_queries, int64_t n_rows, in
   WorkspaceCarver ws(nullptr);
   ws.take<int>(64);
   ws.take<float>((size_t)n_queries * d);
-  const size_t lists = (size_t)n_queries * kp.n_blocks * kConsumerWarps * k;
+  const size_t lists = (size_t)n_queries * kp.n_blocks * k;
   ws.take<float>(lists);
   ws.take<int>(lists);
   return ws.total();
@@ -979,7 +1001,7 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
   WorkspaceCarver ws(workspace);
   int* counter = ws.take<int>(64);
   float* qn = ws.take<float>((size_t)n_queries * d);
-  const size_t lists = (size_t)n_queries * kp.n_blocks * kConsumerWarps * k;
+  const size_t lists = (size_t)n_queries * kp.n_blocks * k;
   float* part_d = ws.take<float>(lists);
   int* part_id = ws.take<int>(lists);
 
@@ -1026,7 +1048,8 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
     NLSH_CUDA_TRY(nlsh_post_launch());
   }
   return launch_merge_partials(part_d, part_id, nullptr, nullptr, 1, 1, k, kp.rchunk, kp.n_blocks, 1,
-                               n_queries, id_offset, ids_out, dists_out, nullptr, st);
+                               metric == NLSH_METRIC_L2 ? 1 : 0, n_queries, id_offset, ids_out,
+                               dists_out, nullptr, st);
 }
 
 extern "C" int nlsh_merge_topk(const float* dists, const int64_t* ids, int32_t n_lists,
