@@ -23,6 +23,7 @@
 // All top-k decisions use the (distance, id) lexicographic order, so the result does not
 // depend on item scheduling or on how many GPUs the database is sharded over.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -34,36 +35,59 @@ constexpr int kTileRows = 32 * kConsumerWarps;  // rows per stage
 constexpr int kG = 8;                           // queries per item
 constexpr int kBoxCols = 32;                    // TMA box: 32 floats = one 128-byte swizzle row
 constexpr int kBoxFloats = kTileRows * kBoxCols;  // 16 KB per box
-constexpr int kBoxesPerStage = 2;               // a stage holds 64 columns of 128 rows (32 KB)
+constexpr int kMaxBoxesPerStage = 2;            // a stage holds up to 64 columns of 128 rows (32 KB)
 constexpr int kMaxChunksPerBucket = 64;
 constexpr int kListsPerWarp = kG / kConsumerWarps;  // queries whose top-k a warp owns
 constexpr size_t kExchangeBytes = 2 * (kG + 1) * kTileRows * sizeof(float);
-constexpr int kCtasPerSm = 2;
-constexpr size_t kSmemBudget = 112 * 1024;  // per CTA, leaves room for 2 CTAs / SM
+constexpr size_t kSmemPerSm = 227 * 1024;
 
 struct ScanGeom {
   int d;         // real columns
   int d_pad;     // row stride of x_sorted (multiple of 4)
   int n_boxes;   // ceil(d_pad / 32) column boxes per row tile
-  int n_chunks;  // ceil(n_boxes / kBoxesPerStage) stages per row tile
+  int bps;       // boxes per stage
+  int n_chunks;  // ceil(n_boxes / bps) stages per row tile
   int stages;
+  int ctas_per_sm;
   size_t smem_bytes;
 };
 
-ScanGeom scan_geom(int d, bool async) {
+// Occupancy plan: k <= 64 kernels are compiled for 3 CTAs / SM (<= 136 registers), the
+// k <= 128 ones for 2.  NLSH_SCAN_TUNE="boxes_per_stage,stages,ctas_per_sm" overrides it
+// (experiments only).
+int scan_max_ctas(int k) { return k <= 64 ? 3 : 2; }
+
+ScanGeom scan_geom(int d, int k, bool async) {
   ScanGeom g;
   g.d = d;
   g.d_pad = (d + 3) / 4 * 4;
   g.n_boxes = (g.d_pad + kBoxCols - 1) / kBoxCols;
-  g.n_chunks = (g.n_boxes + kBoxesPerStage - 1) / kBoxesPerStage;
-  const size_t stage_bytes = (size_t)kBoxesPerStage * kBoxFloats * sizeof(float);
+  g.ctas_per_sm = scan_max_ctas(k);
+  g.bps = 1;
+  int want_stages = 3;
+  if (const char* env = getenv("NLSH_SCAN_TUNE")) {
+    int b = 0, st = 0, c = 0;
+    if (sscanf(env, "%d,%d,%d", &b, &st, &c) == 3) {
+      if (b >= 1 && b <= kMaxBoxesPerStage) g.bps = b;
+      if (st >= 2 && st <= 4) want_stages = st;
+      if (c >= 1 && c <= scan_max_ctas(k)) g.ctas_per_sm = c;
+    }
+  }
+  if (g.bps > g.n_boxes) g.bps = g.n_boxes;
+  g.n_chunks = (g.n_boxes + g.bps - 1) / g.bps;
+  const size_t stage_bytes = (size_t)g.bps * kBoxFloats * sizeof(float);
   const size_t q_bytes = (size_t)kG * g.d_pad * sizeof(float);
   // + score/id exchange (double buffered) + barriers/item slots + 1024-byte alignment slack
   const size_t fixed = q_bytes + kExchangeBytes + 256 + 1024;
   g.stages = 1;
   if (async) {
-    g.stages = 4;
-    while (g.stages > 2 && fixed + g.stages * stage_bytes > kSmemBudget) --g.stages;
+    g.stages = want_stages;
+    // fit ctas_per_sm CTAs (each also pays 1 KB of driver-reserved shared memory)
+    while (g.ctas_per_sm > 1 &&
+           (fixed + 2 * stage_bytes + 1024) * g.ctas_per_sm > kSmemPerSm)
+      --g.ctas_per_sm;
+    while (g.stages > 2 && (fixed + g.stages * stage_bytes + 1024) * g.ctas_per_sm > kSmemPerSm)
+      --g.stages;
   }
   g.smem_bytes = fixed + g.stages * stage_bytes;
   return g;
@@ -76,7 +100,7 @@ struct ScanPolicy {
 
 ScanPolicy scan_policy(int64_t n_queries, int p, int n_buckets, int64_t n_rows,
                        int64_t max_bucket_rows) {
-  const int64_t grid = (int64_t)nlsh_num_sms() * kCtasPerSm;
+  const int64_t grid = (int64_t)nlsh_num_sms() * 2;
   const int64_t target_items = grid * 8;
   const int64_t pairs = n_queries * p > 0 ? n_queries * p : 1;
   const int64_t distinct = pairs < n_buckets ? pairs : n_buckets;
@@ -121,7 +145,7 @@ struct ScanArgs {
   int dense_qgroups;
   int dense_items;
   int exclude_self;
-  int d, d_pad, n_boxes, n_chunks, stages;
+  int d, d_pad, n_boxes, bps, n_chunks, stages;
 };
 
 // ---- per-box distance accumulation --------------------------------------------------------
@@ -288,13 +312,14 @@ __device__ __forceinline__ Item decode_item(const ScanArgs& a, int item) {
 // TMA tensor copies.  !ASYNC (debug / A-B): 4 warps stage each chunk cooperatively with plain
 // loads into the same swizzled layout.
 template <int METRIC, int KPL, bool ASYNC>
-__global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kConsumerWarps, kCtasPerSm)
+__global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kConsumerWarps,
+                                  KPL <= 2 ? 3 : 2)
     scan_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B boxes need 1024-byte aligned shared addresses
   unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* stage_buf = reinterpret_cast<float*>(smem_al);
-  constexpr size_t stage_floats = (size_t)kBoxesPerStage * kBoxFloats;
+  const size_t stage_floats = (size_t)a.bps * kBoxFloats;
   float* qs = stage_buf + (size_t)a.stages * stage_floats;
   float* score_s = qs + (size_t)kG * a.d_pad;                           // [2][kG][kTileRows]
   int* id_s = reinterpret_cast<int*>(score_s + 2 * kG * kTileRows);     // [2][kTileRows]
@@ -368,8 +393,8 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
         Acc acc;
         acc.clear();
         for (int ch = 0; ch < a.n_chunks; ++ch) {
-          const int box0 = ch * kBoxesPerStage;
-          const int nb = (a.n_boxes - box0) < kBoxesPerStage ? (a.n_boxes - box0) : kBoxesPerStage;
+          const int box0 = ch * a.bps;
+          const int nb = (a.n_boxes - box0) < a.bps ? (a.n_boxes - box0) : a.bps;
           const int s = ASYNC ? (int)(ring % (unsigned)a.stages) : 0;
           float* stage = stage_buf + s * stage_floats;
           if (ASYNC) {
@@ -451,8 +476,8 @@ __global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kCons
         for (int t = 0; t < n_tiles; ++t) {
           const int tile_row0 = (int)(it.row0 + (long long)t * kTileRows);
           for (int ch = 0; ch < a.n_chunks; ++ch) {
-            const int box0 = ch * kBoxesPerStage;
-            const int nb = (a.n_boxes - box0) < kBoxesPerStage ? (a.n_boxes - box0) : kBoxesPerStage;
+            const int box0 = ch * a.bps;
+            const int nb = (a.n_boxes - box0) < a.bps ? (a.n_boxes - box0) : a.bps;
             const int s = (int)(ring % (unsigned)a.stages);
             mbar_wait(&empty_bar[s], ((ring / (unsigned)a.stages) & 1u) ^ 1u);
             // a box is always written in full (rows / columns past the tensor are zero filled)
@@ -847,7 +872,7 @@ KnnPlan knn_plan(int64_t n_queries, int64_t n_rows) {
   KnnPlan kp;
   kp.qgroups = (int)((n_queries + kG - 1) / kG);
   if (kp.qgroups < 1) kp.qgroups = 1;
-  const int64_t grid = (int64_t)nlsh_num_sms() * kCtasPerSm;
+  const int64_t grid = (int64_t)nlsh_num_sms() * 2;
   int64_t blocks = (grid * 8 + kp.qgroups - 1) / kp.qgroups;
   const int64_t max_blocks = (n_rows + kTileRows - 1) / kTileRows;
   if (blocks > max_blocks) blocks = max_blocks;
@@ -903,7 +928,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool async = (flags & 1u) == 0;
-  const ScanGeom geom = scan_geom(d, async);
+  const ScanGeom geom = scan_geom(d, k, async);
   const long long n_pairs = (long long)n_queries * p;
 
   NLSH_CUDA_TRY(cudaMemsetAsync(w.cnt, 0, w.zero_ints * sizeof(int), st));
@@ -949,9 +974,10 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   a.d = geom.d;
   a.d_pad = geom.d_pad;
   a.n_boxes = geom.n_boxes;
+  a.bps = geom.bps;
   a.n_chunks = geom.n_chunks;
   a.stages = geom.stages;
-  const int grid = nlsh_num_sms() * kCtasPerSm;
+  const int grid = nlsh_num_sms() * geom.ctas_per_sm;
   nlsh_profile_mark(st, true);
   int rc = launch_scan_metric(metric, a, geom, async, grid, st);
   nlsh_profile_mark(st, false);
@@ -1013,7 +1039,7 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
     NLSH_CUDA_TRY(nlsh_post_launch());
     q_used = qn;
   }
-  const ScanGeom geom = scan_geom(d, true);
+  const ScanGeom geom = scan_geom(d, k, true);
   ScanArgs a{};
   a.xs = xdb;
   a.ids = nullptr;
@@ -1036,9 +1062,10 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
   a.d = geom.d;
   a.d_pad = geom.d_pad;
   a.n_boxes = geom.n_boxes;
+  a.bps = geom.bps;
   a.n_chunks = geom.n_chunks;
   a.stages = geom.stages;
-  const int grid = nlsh_num_sms() * kCtasPerSm;
+  const int grid = nlsh_num_sms() * geom.ctas_per_sm;
   if (n_rows > 0) {
     int rc = launch_scan_metric(metric, a, geom, true, grid, st);
     if (rc != NLSH_OK) return rc;
