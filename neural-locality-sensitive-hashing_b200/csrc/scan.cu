@@ -41,6 +41,16 @@ constexpr int kListsPerWarp = kG / kConsumerWarps;  // queries whose top-k a war
 constexpr size_t kExchangeBytes = 2 * (kG + 1) * kTileRows * sizeof(float);
 constexpr size_t kSmemPerSm = 227 * 1024;
 
+// One work item as the scan kernel consumes it (64 bytes, written by plan_items_kernel).
+struct __align__(16) ItemRec {
+  int row0, row1;  // rows of x_sorted covered by this item
+  int ng;          // queries in this item (1..kG); 0 = end-of-work sentinel (shared memory only)
+  int chunk;       // chunk index inside the bucket / dense row block
+  int f[kG];       // flat probe index q * p + j (probe mode) or query index (dense); -1 unused
+  int pad[4];
+};
+static_assert(sizeof(ItemRec) == 64, "ItemRec must be 64 bytes");
+
 struct ScanGeom {
   int d;         // real columns
   int d_pad;     // row stride of x_sorted (multiple of 4)
@@ -48,6 +58,7 @@ struct ScanGeom {
   int bps;       // boxes per stage
   int n_chunks;  // ceil(n_boxes / bps) stages per row tile
   int stages;
+  int nqb;       // item / query ring depth (2, or 1 when the queries are too wide)
   int ctas_per_sm;
   size_t smem_bytes;
 };
@@ -77,19 +88,22 @@ ScanGeom scan_geom(int d, int k, bool async) {
   g.n_chunks = (g.n_boxes + g.bps - 1) / g.bps;
   const size_t stage_bytes = (size_t)g.bps * kBoxFloats * sizeof(float);
   const size_t q_bytes = (size_t)kG * g.d_pad * sizeof(float);
-  // + score/id exchange (double buffered) + barriers/item slots + 1024-byte alignment slack
-  const size_t fixed = q_bytes + kExchangeBytes + 256 + 1024;
+  // score/id exchange (double buffered) + item records + barriers + 1024-byte alignment slack
+  const size_t misc = kExchangeBytes + 2 * sizeof(ItemRec) + 256 + 1024;
   g.stages = 1;
+  g.nqb = 1;
   if (async) {
     g.stages = want_stages;
-    // fit ctas_per_sm CTAs (each also pays 1 KB of driver-reserved shared memory)
-    while (g.ctas_per_sm > 1 &&
-           (fixed + 2 * stage_bytes + 1024) * g.ctas_per_sm > kSmemPerSm)
-      --g.ctas_per_sm;
-    while (g.stages > 2 && (fixed + g.stages * stage_bytes + 1024) * g.ctas_per_sm > kSmemPerSm)
-      --g.stages;
+    g.nqb = 2;
+    // fit ctas_per_sm CTAs (each also pays 1 KB of driver-reserved shared memory): first give up
+    // the second query buffer, then CTAs, then stages
+    auto need = [&](int nqb, int stages) { return nqb * q_bytes + misc + stages * stage_bytes + 1024; };
+    if (need(2, 2) * g.ctas_per_sm > kSmemPerSm) g.nqb = 1;
+    while (g.ctas_per_sm > 1 && need(g.nqb, 2) * g.ctas_per_sm > kSmemPerSm) --g.ctas_per_sm;
+    if (g.nqb == 1 && need(2, 2) * g.ctas_per_sm <= kSmemPerSm) g.nqb = 2;
+    while (g.stages > 2 && need(g.nqb, g.stages) * g.ctas_per_sm > kSmemPerSm) --g.stages;
   }
-  g.smem_bytes = fixed + g.stages * stage_bytes;
+  g.smem_bytes = g.nqb * q_bytes + misc + g.stages * stage_bytes;
   return g;
 }
 
@@ -130,6 +144,7 @@ struct ScanArgs {
   const int* pair_off;
   const int* pairs;
   const int* item_off;
+  const ItemRec* items;
   int* item_counter;
   float* part_d;
   int* part_id;
@@ -145,7 +160,7 @@ struct ScanArgs {
   int dense_qgroups;
   int dense_items;
   int exclude_self;
-  int d, d_pad, n_boxes, bps, n_chunks, stages;
+  int d, d_pad, n_boxes, bps, n_chunks, stages, nqb;
 };
 
 // ---- per-box distance accumulation --------------------------------------------------------
@@ -265,6 +280,7 @@ struct Item {
   int pair_base;         // probe mode: first entry of `pairs`; dense: first query index
 };
 
+
 __device__ __forceinline__ Item decode_item(const ScanArgs& a, int item) {
   Item it;
   if (a.dense) {
@@ -308,189 +324,312 @@ __device__ __forceinline__ Item decode_item(const ScanArgs& a, int item) {
   return it;
 }
 
-// Scan kernel.  ASYNC: warps 0..3 consume, one elected thread of warp 4 produces with 2-D
-// TMA tensor copies.  !ASYNC (debug / A-B): 4 warps stage each chunk cooperatively with plain
-// loads into the same swizzled layout.
-template <int METRIC, int KPL, bool ASYNC>
-__global__ void __launch_bounds__(ASYNC ? 32 * (kConsumerWarps + 1) : 32 * kConsumerWarps,
-                                  KPL <= 2 ? 3 : 2)
+// Expands item index -> ItemRec (the binary search over item_off runs here, thousands of
+// threads wide, instead of on the scan kernel's critical path).
+__global__ void plan_items_kernel(const ScanArgs a, ItemRec* __restrict__ out, int max_items) {
+  int total = a.dense ? a.dense_items : a.item_off[a.n_buckets];
+  if (total > max_items) total = max_items;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const Item it = decode_item(a, i);
+    ItemRec r;
+    r.row0 = (int)it.row0;
+    r.row1 = (int)it.row1;
+    r.ng = it.ng;
+    r.chunk = it.chunk;
+#pragma unroll
+    for (int g = 0; g < kG; ++g)
+      r.f[g] = g < it.ng ? (a.dense ? it.pair_base + g : a.pairs[it.pair_base + g]) : -1;
+    r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = 0;
+    out[i] = r;
+  }
+}
+
+// ---- pieces shared by the two scan kernels --------------------------------------------------
+template <int KPL>
+struct ItemLists {
+  WarpTopK<KPL, int> top[kListsPerWarp];  // lists of queries g = warp + kConsumerWarps * i
+  int self_id[kListsPerWarp];
+
+  __device__ __forceinline__ void init(const ScanArgs& a, const int* f, int ng, int warp) {
+#pragma unroll
+    for (int i = 0; i < kListsPerWarp; ++i) {
+      top[i].init(NLSH_ID_SENTINEL);
+      const int g = warp + kConsumerWarps * i;
+      self_id[i] = (a.exclude_self && g < ng) ? (int)(a.self_offset + f[g]) : -1;
+    }
+  }
+
+  // Row tile epilogue: scores of the 128 rows x ng queries go through shared memory to the
+  // warp that owns each query's list (buffers double-buffered on `parity`: one named barrier
+  // per tile is enough).
+  template <int METRIC>
+  __device__ __forceinline__ void tile_epilogue(const Acc& acc, float* score_s, int* id_s, int parity,
+                                                int r_local, int cand_id, bool valid, int ng,
+                                                int warp, int lane, int k) {
+    float* sc = score_s + parity * (kG * kTileRows);
+    int* idb = id_s + parity * kTileRows;
+    const float xx = acc.sum_xx();
+    idb[r_local] = valid ? cand_id : NLSH_ID_SENTINEL;
+#pragma unroll
+    for (int g = 0; g < kG; ++g)
+      if (g < ng) sc[g * kTileRows + r_local] = finalize_distance<METRIC>(acc.sum(g), xx);
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory");
+#pragma unroll
+    for (int i = 0; i < kListsPerWarp; ++i) {
+      const int g = warp + kConsumerWarps * i;
+      if (g < ng) {
+#pragma unroll
+        for (int j = 0; j < kTileRows / 32; ++j) {
+          const int r = lane + 32 * j;
+          const int cid = idb[r];
+          top[i].offer(sc[g * kTileRows + r], cid, cid != NLSH_ID_SENTINEL && cid != self_id[i], k);
+        }
+      }
+    }
+  }
+
+  // Partial lists: one per (query-probe, chunk).
+  __device__ __forceinline__ void write_out(const ScanArgs& a, const int* f, int ng, int chunk,
+                                            int warp, int lane) const {
+#pragma unroll
+    for (int i = 0; i < kListsPerWarp; ++i) {
+      const int g = warp + kConsumerWarps * i;
+      if (g < ng) {
+        const size_t slot = (size_t)f[g] * a.max_chunks + chunk;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+          const int pos = j * 32 + lane;
+          if (pos < a.k) {
+            a.part_d[slot * a.k + pos] = top[i].d[j];
+            a.part_id[slot * a.k + pos] = top[i].id[j];
+          }
+        }
+      }
+    }
+  }
+};
+
+__device__ __forceinline__ unsigned char* align_smem_1024(unsigned char* p) {
+  return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u);  // SWIZZLE_128B boxes need 1024-byte alignment
+}
+
+// Distances of this thread's row against the stage's boxes.
+template <int METRIC>
+__device__ __forceinline__ void consume_stage(const ScanArgs& a, Acc& acc, const float* stage, int box0,
+                                              int nb, int r_local, int xr, const float* qs, int ng) {
+  for (int b = 0; b < nb; ++b) {
+    const int col0 = (box0 + b) * kBoxCols;
+    int cols = a.d - col0;  // valid (unpadded) columns of this box
+    if (cols > kBoxCols) cols = kBoxCols;
+    if (cols <= 0) break;
+    consume_dispatch<METRIC>(ng, acc, stage + b * kBoxFloats + r_local * kBoxCols, xr, qs + col0,
+                             a.d_pad, cols >> 2, cols & 3);
+  }
+}
+
+// ---- the scan kernel ------------------------------------------------------------------------
+// Warps 0..3 consume; lane 0 of warp 4 is the producer.  The producer owns the work queue: it
+// pulls item indices from the global atomic counter and, per item, publishes the 64-byte item
+// record + the item's query vectors (1-D bulk copies) through a 2-deep item ring
+// (q_full / q_empty mbarriers), then streams the item's row tiles with 2-D TMA tensor copies into
+// the stage ring (full / empty mbarriers).  Both rings run across item boundaries, so the
+// pipeline never drains and the consumers never touch global memory except for the row ids.
+template <int METRIC, int KPL>
+__global__ void __launch_bounds__(32 * (kConsumerWarps + 1), KPL <= 2 ? 3 : 2)
     scan_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ unsigned char smem_raw[];
-  // SWIZZLE_128B boxes need 1024-byte aligned shared addresses
-  unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* stage_buf = reinterpret_cast<float*>(smem_al);
+  float* stage_buf = reinterpret_cast<float*>(align_smem_1024(smem_raw));
   const size_t stage_floats = (size_t)a.bps * kBoxFloats;
-  float* qs = stage_buf + (size_t)a.stages * stage_floats;
-  float* score_s = qs + (size_t)kG * a.d_pad;                           // [2][kG][kTileRows]
-  int* id_s = reinterpret_cast<int*>(score_s + 2 * kG * kTileRows);     // [2][kTileRows]
-  unsigned char* tail_ptr = reinterpret_cast<unsigned char*>(id_s + 2 * kTileRows);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail_ptr);  // [stages <= 4]
-  uint64_t* empty_bar = full_bar + 4;                          // [stages <= 4]
-  int* s_f = reinterpret_cast<int*>(empty_bar + 4);            // [kG] flat probe index / query
-  int* s_item = s_f + kG;                                      // [2]
+  float* qbuf = stage_buf + (size_t)a.stages * stage_floats;               // [nqb][kG][d_pad]
+  float* score_s = qbuf + (size_t)a.nqb * kG * a.d_pad;                    // [2][kG][kTileRows]
+  int* id_s = reinterpret_cast<int*>(score_s + 2 * kG * kTileRows);        // [2][kTileRows]
+  ItemRec* itm = reinterpret_cast<ItemRec*>(id_s + 2 * kTileRows);         // [nqb]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(itm + 2);               // [stages <= 4]
+  uint64_t* empty_bar = full_bar + 4;                                      // [stages <= 4]
+  uint64_t* q_full = empty_bar + 4;                                        // [nqb <= 2]
+  uint64_t* q_empty = q_full + 2;                                          // [nqb <= 2]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
-  if (ASYNC && tid == 0) {
+  if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kConsumerWarps);
     }
+    for (int s = 0; s < a.nqb; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], kConsumerWarps);
+    }
     mbar_fence_init();
   }
-  const int total_items = a.dense ? a.dense_items : a.item_off[a.n_buckets];
-  if (tid == 0) s_item[0] = atomicAdd(a.item_counter, 1);
   __syncthreads();
 
-  unsigned ring = 0;  // stage uses so far (same sequence in producer and consumers)
-  int round = 0;
-  int item = s_item[0];
-
-  while (item < total_items) {
-    if (tid == 0) s_item[(round + 1) & 1] = atomicAdd(a.item_counter, 1);
-    const Item it = decode_item(a, item);
-    const int n_tiles = (int)((it.row1 - it.row0 + kTileRows - 1) / kTileRows);
-
-    if (warp < kConsumerWarps) {
-      // ---- stage the item's queries: qs[g][0..d_pad) -----------------------------------
-      const int ctid = tid;  // 0..127
-      if (ctid < kG) {
-        int f = -1;
-        if (ctid < it.ng) f = a.dense ? it.pair_base + ctid : a.pairs[it.pair_base + ctid];
-        s_f[ctid] = f;
+  if (warp == kConsumerWarps) {
+    // =================================== producer =========================================
+    if (lane != 0) return;
+    const int total_items = a.dense ? a.dense_items : a.item_off[a.n_buckets];
+    const unsigned q_bytes = (unsigned)a.d_pad * sizeof(float);
+    unsigned ring = 0, icount = 0;
+    while (true) {
+      const int item = atomicAdd(a.item_counter, 1);
+      const int islot = (int)(icount % (unsigned)a.nqb);
+      mbar_wait(&q_empty[islot], ((icount / (unsigned)a.nqb) & 1u) ^ 1u);
+      ItemRec* dst = &itm[islot];
+      if (item >= total_items) {
+        dst->ng = 0;  // end of work
+        mbar_arrive(&q_full[islot]);
+        break;
       }
-      for (int g = 0; g < kG; ++g) {
-        int qidx = -1;
-        if (g < it.ng) {
-          const int f = a.dense ? it.pair_base + g : a.pairs[it.pair_base + g];
-          qidx = a.dense ? f : f / a.p;
-        }
-        for (int c = ctid; c < a.d_pad; c += 32 * kConsumerWarps)
-          qs[g * a.d_pad + c] = (qidx >= 0 && c < a.d) ? a.q[(size_t)qidx * a.d + c] : 0.f;
+      const ItemRec rec = a.items[item];
+      *dst = rec;
+      mbar_arrive_expect_tx(&q_full[islot], (unsigned)rec.ng * q_bytes);
+      float* qdst = qbuf + (size_t)islot * kG * a.d_pad;
+      for (int g = 0; g < rec.ng; ++g) {
+        const int qidx = a.dense ? rec.f[g] : rec.f[g] / a.p;
+        bulk_g2s(qdst + g * a.d_pad, a.q + (size_t)qidx * a.d_pad, q_bytes, &q_full[islot]);
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory");
-
-      // this warp owns the lists of queries g = warp + kConsumerWarps * i
-      WarpTopK<KPL, int> top[kListsPerWarp];
-      int self_id[kListsPerWarp];
-#pragma unroll
-      for (int i = 0; i < kListsPerWarp; ++i) {
-        top[i].init(NLSH_ID_SENTINEL);
-        const int g = warp + kConsumerWarps * i;
-        self_id[i] = (a.exclude_self && g < it.ng) ? (int)(a.self_offset + s_f[g]) : -1;
-      }
-
-      const int r_local = warp * 32 + lane;
-      const int xr = r_local & 7;
+      const int n_tiles = (rec.row1 - rec.row0 + kTileRows - 1) / kTileRows;
       for (int t = 0; t < n_tiles; ++t) {
-        const long long tile_row0 = it.row0 + (long long)t * kTileRows;
-        const long long row = tile_row0 + r_local;
-        const bool valid = row < it.row1;
-        int cand_id = NLSH_ID_SENTINEL;
-        if (valid) cand_id = a.ids ? a.ids[row] : (int)row;  // latency hidden behind the chunk loop
-        Acc acc;
-        acc.clear();
+        const int tile_row0 = rec.row0 + t * kTileRows;
         for (int ch = 0; ch < a.n_chunks; ++ch) {
           const int box0 = ch * a.bps;
           const int nb = (a.n_boxes - box0) < a.bps ? (a.n_boxes - box0) : a.bps;
-          const int s = ASYNC ? (int)(ring % (unsigned)a.stages) : 0;
-          float* stage = stage_buf + s * stage_floats;
-          if (ASYNC) {
-            mbar_wait(&full_bar[s], (ring / (unsigned)a.stages) & 1u);
-          } else {
-            // same layout as the TMA boxes: box-major, 128-byte rows, chunk ^= (row & 7)
-            const int rows_in_tile =
-                (int)((it.row1 - tile_row0) < kTileRows ? (it.row1 - tile_row0) : kTileRows);
-            const int cols = (a.d_pad - box0 * kBoxCols) < nb * kBoxCols ? (a.d_pad - box0 * kBoxCols)
-                                                                       : nb * kBoxCols;
-            const int cvec = cols >> 2;
-            for (int idx = tid; idx < rows_in_tile * cvec; idx += 32 * kConsumerWarps) {
-              const int r = idx / cvec, v = idx - r * cvec;
-              const float4 val = __ldcs(reinterpret_cast<const float4*>(
-                                            a.xs + (size_t)(tile_row0 + r) * a.d_pad + box0 * kBoxCols) + v);
-              const int b = v >> 3, c = v & 7;
-              *reinterpret_cast<float4*>(stage + b * kBoxFloats + r * kBoxCols + ((c ^ (r & 7)) << 2)) = val;
-            }
-            __syncthreads();
-          }
-          for (int b = 0; b < nb; ++b) {
-            const int col0 = (box0 + b) * kBoxCols;
-            int cols = a.d - col0;  // valid (unpadded) columns of this box
-            if (cols > kBoxCols) cols = kBoxCols;
-            if (cols <= 0) break;
-            consume_dispatch<METRIC>(it.ng, acc, stage + b * kBoxFloats + r_local * kBoxCols, xr,
-                                     qs + col0, a.d_pad, cols >> 2, cols & 3);
-          }
-          if (ASYNC) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
-          } else {
-            __syncthreads();
-          }
+          const int s = (int)(ring % (unsigned)a.stages);
+          mbar_wait(&empty_bar[s], ((ring / (unsigned)a.stages) & 1u) ^ 1u);
+          // a box is always written in full (rows / columns past the tensor are zero filled)
+          mbar_arrive_expect_tx(&full_bar[s], (unsigned)(nb * kBoxFloats * sizeof(float)));
+          float* sdst = stage_buf + s * stage_floats;
+          for (int b = 0; b < nb; ++b)
+            tma_load_2d(sdst + b * kBoxFloats, &tmap, (box0 + b) * kBoxCols, tile_row0, &full_bar[s]);
           ++ring;
         }
-        // ---- exchange: row-major scores -> the warp that owns each query's list ----------
-        // (double buffered on the tile parity: one named barrier per tile is enough)
-        float* sc = score_s + (t & 1) * (kG * kTileRows);
-        int* idb = id_s + (t & 1) * kTileRows;
-        const float xx = acc.sum_xx();
-        idb[r_local] = valid ? cand_id : NLSH_ID_SENTINEL;
-#pragma unroll
-        for (int g = 0; g < kG; ++g)
-          if (g < it.ng) sc[g * kTileRows + r_local] = finalize_distance<METRIC>(acc.sum(g), xx);
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory");
-#pragma unroll
-        for (int i = 0; i < kListsPerWarp; ++i) {
-          const int g = warp + kConsumerWarps * i;
-          if (g < it.ng) {
-#pragma unroll
-            for (int j = 0; j < kTileRows / 32; ++j) {
-              const int r = lane + 32 * j;
-              const int cid = idb[r];
-              top[i].offer(sc[g * kTileRows + r], cid, cid != NLSH_ID_SENTINEL && cid != self_id[i], a.k);
-            }
-          }
-        }
       }
-      // ---- partial lists: one per (query-probe, chunk) ---------------------------------
-#pragma unroll
-      for (int i = 0; i < kListsPerWarp; ++i) {
-        const int g = warp + kConsumerWarps * i;
-        if (g < it.ng) {
-          const size_t slot = (size_t)s_f[g] * a.max_chunks + it.chunk;
-#pragma unroll
-          for (int j = 0; j < KPL; ++j) {
-            const int pos = j * 32 + lane;
-            if (pos < a.k) {
-              a.part_d[slot * a.k + pos] = top[i].d[j];
-              a.part_id[slot * a.k + pos] = top[i].id[j];
-            }
-          }
-        }
-      }
-    } else if (ASYNC) {
-      // ---- producer: one elected thread streams the item's row tiles, stage by stage -----
-      if (lane == 0) {
-        for (int t = 0; t < n_tiles; ++t) {
-          const int tile_row0 = (int)(it.row0 + (long long)t * kTileRows);
-          for (int ch = 0; ch < a.n_chunks; ++ch) {
-            const int box0 = ch * a.bps;
-            const int nb = (a.n_boxes - box0) < a.bps ? (a.n_boxes - box0) : a.bps;
-            const int s = (int)(ring % (unsigned)a.stages);
-            mbar_wait(&empty_bar[s], ((ring / (unsigned)a.stages) & 1u) ^ 1u);
-            // a box is always written in full (rows / columns past the tensor are zero filled)
-            mbar_arrive_expect_tx(&full_bar[s], (unsigned)(nb * kBoxFloats * sizeof(float)));
-            float* dst = stage_buf + s * stage_floats;
-            for (int b = 0; b < nb; ++b)
-              tma_load_2d(dst + b * kBoxFloats, &tmap, (box0 + b) * kBoxCols, tile_row0, &full_bar[s]);
-            ++ring;
-          }
-        }
-      }
-      __syncwarp();
+      ++icount;
     }
+    return;
+  }
+
+  // ===================================== consumers ==========================================
+  const int r_local = warp * 32 + lane;
+  const int xr = r_local & 7;
+  unsigned ring = 0, icount = 0, tcount = 0;
+  while (true) {
+    const int islot = (int)(icount % (unsigned)a.nqb);
+    mbar_wait(&q_full[islot], (icount / (unsigned)a.nqb) & 1u);
+    const ItemRec* rec = &itm[islot];
+    const int ng = rec->ng;
+    if (ng == 0) break;
+    const int row0 = rec->row0, row1 = rec->row1;
+    const float* qs = qbuf + (size_t)islot * kG * a.d_pad;
+    ItemLists<KPL> lists;
+    lists.init(a, rec->f, ng, warp);
+    const int n_tiles = (row1 - row0 + kTileRows - 1) / kTileRows;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int row = row0 + t * kTileRows + r_local;
+      const bool valid = row < row1;
+      int cand_id = NLSH_ID_SENTINEL;
+      if (valid) cand_id = a.ids ? a.ids[row] : row;  // latency hidden behind the chunk loop
+      Acc acc;
+      acc.clear();
+      for (int ch = 0; ch < a.n_chunks; ++ch) {
+        const int box0 = ch * a.bps;
+        const int nb = (a.n_boxes - box0) < a.bps ? (a.n_boxes - box0) : a.bps;
+        const int s = (int)(ring % (unsigned)a.stages);
+        mbar_wait(&full_bar[s], (ring / (unsigned)a.stages) & 1u);
+        consume_stage<METRIC>(a, acc, stage_buf + s * stage_floats, box0, nb, r_local, xr, qs, ng);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        ++ring;
+      }
+      lists.template tile_epilogue<METRIC>(acc, score_s, id_s, (int)(tcount & 1u), r_local, cand_id,
+                                           valid, ng, warp, lane, a.k);
+      ++tcount;
+    }
+    lists.write_out(a, rec->f, ng, rec->chunk, warp, lane);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&q_empty[islot]);
+    ++icount;
+  }
+}
+
+// Debug / A-B variant without TMA or mbarriers: 4 warps stage every chunk cooperatively with
+// plain loads into the same swizzled layout (flags bit 0 of nlsh_query_scan_topk).
+template <int METRIC, int KPL>
+__global__ void __launch_bounds__(32 * kConsumerWarps, 2) scan_kernel_sync(const ScanArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  float* stage_buf = reinterpret_cast<float*>(align_smem_1024(smem_raw));
+  const size_t stage_floats = (size_t)a.bps * kBoxFloats;
+  float* qs = stage_buf + stage_floats;                               // [kG][d_pad]
+  float* score_s = qs + (size_t)kG * a.d_pad;                         // [2][kG][kTileRows]
+  int* id_s = reinterpret_cast<int*>(score_s + 2 * kG * kTileRows);   // [2][kTileRows]
+  ItemRec* itm = reinterpret_cast<ItemRec*>(id_s + 2 * kTileRows);    // [1]
+  int* s_item = reinterpret_cast<int*>(itm + 2);                      // [2]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int total_items = a.dense ? a.dense_items : a.item_off[a.n_buckets];
+  if (tid == 0) s_item[0] = atomicAdd(a.item_counter, 1);
+  __syncthreads();
+  int round = 0;
+  int item = s_item[0];
+  const int r_local = warp * 32 + lane;
+  const int xr = r_local & 7;
+  unsigned tcount = 0;
+
+  while (item < total_items) {
+    if (tid == 0) {
+      s_item[(round + 1) & 1] = atomicAdd(a.item_counter, 1);
+      itm[0] = a.items[item];
+    }
+    __syncthreads();
+    const ItemRec* rec = &itm[0];
+    const int ng = rec->ng;
+    const int row0 = rec->row0, row1 = rec->row1;
+    for (int g = 0; g < kG; ++g) {
+      int qidx = -1;
+      if (g < ng) qidx = a.dense ? rec->f[g] : rec->f[g] / a.p;
+      for (int c = tid; c < a.d_pad; c += 32 * kConsumerWarps)
+        qs[g * a.d_pad + c] = qidx >= 0 ? a.q[(size_t)qidx * a.d_pad + c] : 0.f;
+    }
+    __syncthreads();
+    ItemLists<KPL> lists;
+    lists.init(a, rec->f, ng, warp);
+    const int n_tiles = (row1 - row0 + kTileRows - 1) / kTileRows;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int tile_row0 = row0 + t * kTileRows;
+      const int row = tile_row0 + r_local;
+      const bool valid = row < row1;
+      int cand_id = NLSH_ID_SENTINEL;
+      if (valid) cand_id = a.ids ? a.ids[row] : row;
+      Acc acc;
+      acc.clear();
+      const int rows_in_tile = (row1 - tile_row0) < kTileRows ? (row1 - tile_row0) : kTileRows;
+      for (int ch = 0; ch < a.n_chunks; ++ch) {
+        const int box0 = ch * a.bps;
+        const int nb = (a.n_boxes - box0) < a.bps ? (a.n_boxes - box0) : a.bps;
+        // same layout as the TMA boxes: box-major, 128-byte rows, 16-byte chunk ^= (row & 7)
+        const int cols = (a.d_pad - box0 * kBoxCols) < nb * kBoxCols ? (a.d_pad - box0 * kBoxCols)
+                                                                   : nb * kBoxCols;
+        const int cvec = cols >> 2;
+        for (int idx = tid; idx < rows_in_tile * cvec; idx += 32 * kConsumerWarps) {
+          const int r = idx / cvec, v = idx - r * cvec;
+          const float4 val = __ldcs(reinterpret_cast<const float4*>(
+                                        a.xs + (size_t)(tile_row0 + r) * a.d_pad + box0 * kBoxCols) + v);
+          const int b = v >> 3, c = v & 7;
+          *reinterpret_cast<float4*>(stage_buf + b * kBoxFloats + r * kBoxCols + ((c ^ (r & 7)) << 2)) = val;
+        }
+        __syncthreads();
+        consume_stage<METRIC>(a, acc, stage_buf, box0, nb, r_local, xr, qs, ng);
+        __syncthreads();
+      }
+      lists.template tile_epilogue<METRIC>(acc, score_s, id_s, (int)(tcount & 1u), r_local, cand_id,
+                                           valid, ng, warp, lane, a.k);
+      ++tcount;
+    }
+    lists.write_out(a, rec->f, ng, rec->chunk, warp, lane);
     __syncthreads();
     ++round;
     item = s_item[round & 1];
@@ -594,23 +733,30 @@ __global__ void plan_scatter_kernel(const int* __restrict__ probes, const int* _
     pairs[pair_off[b] + atomicAdd(&cursor[b], 1)] = (int)f;
 }
 
-// q / max(|q|, eps) per row (eps = 0: plain normalisation as precompute._cosine_distance).
+// Query staging copy: out[row, 0:d_pad] = q[row, 0:d] (zero padded), optionally scaled by
+// 1 / max(|q|, eps) (mode 1: eps = 1e-8, the cosine_similarity clamp; mode 2: no clamp, as
+// precompute._cosine_distance).  Rows of `out` are 16-byte aligned for the bulk copies.
 __global__ void __launch_bounds__(128)
-    normalize_rows_kernel(const float* __restrict__ q, long long n, int d, float eps,
-                          float* __restrict__ out) {
+    prepare_queries_kernel(const float* __restrict__ q, long long n, int d, int d_pad, int mode,
+                           float* __restrict__ out) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const int lane = lane_id();
-  float ss = 0.f;
-  for (int c = lane; c < d; c += 32) {
-    const float v = q[row * d + c];
-    ss = fmaf(v, v, ss);
-  }
+  float scale = 1.f;
+  if (mode != 0) {
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float v = q[row * d + c];
+      ss = fmaf(v, v, ss);
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(NLSH_FULL_MASK, ss, o);
-  float nrm = sqrtf(ss);
-  if (eps > 0.f) nrm = fmaxf(nrm, eps);
-  for (int c = lane; c < d; c += 32) out[row * d + c] = q[row * d + c] / nrm;
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(NLSH_FULL_MASK, ss, o);
+    float nrm = sqrtf(ss);
+    if (mode == 1) nrm = fmaxf(nrm, 1e-8f);
+    for (int c = lane; c < d_pad; c += 32) out[row * d_pad + c] = c < d ? q[row * d + c] / nrm : 0.f;
+    return;
+  }
+  for (int c = lane; c < d_pad; c += 32) out[row * d_pad + c] = c < d ? q[row * d + c] * scale : 0.f;
 }
 
 // One warp per query: merge the partial lists of its probes (or of the dense row blocks).
@@ -734,15 +880,15 @@ template <int METRIC, int KPL>
 int launch_scan(const ScanArgs& a, const CUtensorMap& tmap, const ScanGeom& g, bool async, int grid,
                 cudaStream_t st) {
   if (async) {
-    auto kern = scan_kernel<METRIC, KPL, true>;
+    auto kern = scan_kernel<METRIC, KPL>;
     NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)g.smem_bytes));
     kern<<<grid, 32 * (kConsumerWarps + 1), g.smem_bytes, st>>>(a, tmap);
   } else {
-    auto kern = scan_kernel<METRIC, KPL, false>;
+    auto kern = scan_kernel_sync<METRIC, KPL>;
     NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)g.smem_bytes));
-    kern<<<grid, 32 * kConsumerWarps, g.smem_bytes, st>>>(a, tmap);
+    kern<<<grid, 32 * kConsumerWarps, g.smem_bytes, st>>>(a);
   }
   return nlsh_check_cuda(nlsh_post_launch(), "scan_kernel launch");
 }
@@ -835,7 +981,9 @@ struct QueryWorkspace {
   int* pair_off;  // [B+1]
   int* item_off;  // [B+1]
   int* pairs;     // [Q*p]
-  float* qn;      // [Q*d]
+  float* qn;      // [Q*d_pad] staged queries
+  ItemRec* items; // [max_items]
+  int max_items;
   float* part_d;
   int* part_id;
   size_t zero_ints;
@@ -854,7 +1002,13 @@ QueryWorkspace carve_query_ws(void* base, int64_t nq, int p, int k, int d, int n
   w.pair_off = ws.take<int>((size_t)n_buckets + 1);
   w.item_off = ws.take<int>((size_t)n_buckets + 1);
   w.pairs = ws.take<int>((size_t)nq * p);
-  w.qn = ws.take<float>((size_t)nq * d);
+  w.qn = ws.take<float>((size_t)nq * ((d + 3) / 4 * 4));
+  // items = sum_b ceil(nq_b / kG) * nch_b <= (pairs / kG + #probed buckets) * max_chunks
+  const int64_t pairs = nq * (int64_t)p;
+  int64_t mi = (pairs / kG + (pairs < n_buckets ? pairs : n_buckets) + 1) * max_chunks;
+  if (mi > (1ll << 30)) mi = 1ll << 30;
+  w.max_items = (int)mi;
+  w.items = ws.take<ItemRec>((size_t)w.max_items);
   const size_t lists = (size_t)nq * p * max_chunks * k;
   w.part_d = ws.take<float>(lists);
   w.part_id = ws.take<int>(lists);
@@ -942,13 +1096,10 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
       probes, offsets, n_buckets, p, n_pairs, w.pair_off, w.cursor, w.pairs);
   NLSH_CUDA_TRY(nlsh_post_launch());
 
-  const float* q_used = xq;
-  if (metric == NLSH_METRIC_ANGULAR) {
-    normalize_rows_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(xq, n_queries, d, 1e-8f,
-                                                                          w.qn);
-    NLSH_CUDA_TRY(nlsh_post_launch());
-    q_used = w.qn;
-  }
+  prepare_queries_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(
+      xq, n_queries, d, geom.d_pad, metric == NLSH_METRIC_ANGULAR ? 1 : 0, w.qn);
+  NLSH_CUDA_TRY(nlsh_post_launch());
+  const float* q_used = w.qn;
 
   ScanArgs a{};
   a.xs = x_sorted;
@@ -958,6 +1109,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   a.pair_off = w.pair_off;
   a.pairs = w.pairs;
   a.item_off = w.item_off;
+  a.items = w.items;
   a.item_counter = w.counter;
   a.part_d = w.part_d;
   a.part_id = w.part_id;
@@ -975,9 +1127,12 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   a.d_pad = geom.d_pad;
   a.n_boxes = geom.n_boxes;
   a.bps = geom.bps;
+  a.nqb = geom.nqb;
   a.n_chunks = geom.n_chunks;
   a.stages = geom.stages;
   const int grid = nlsh_num_sms() * geom.ctas_per_sm;
+  plan_items_kernel<<<nlsh_num_sms() * 4, 256, 0, st>>>(a, w.items, w.max_items);
+  NLSH_CUDA_TRY(nlsh_post_launch());
   nlsh_profile_mark(st, true);
   int rc = launch_scan_metric(metric, a, geom, async, grid, st);
   nlsh_profile_mark(st, false);
@@ -993,6 +1148,7 @@ extern "C" size_t nlsh_knn_workspace_bytes(int64_t n_queries, int64_t n_rows, in
   WorkspaceCarver ws(nullptr);
   ws.take<int>(64);
   ws.take<float>((size_t)n_queries * d);
+  ws.take<ItemRec>((size_t)kp.qgroups * kp.n_blocks);
   const size_t lists = (size_t)n_queries * kp.n_blocks * k;
   ws.take<float>(lists);
   ws.take<int>(lists);
@@ -1027,15 +1183,18 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
   WorkspaceCarver ws(workspace);
   int* counter = ws.take<int>(64);
   float* qn = ws.take<float>((size_t)n_queries * d);
+  const int n_items = kp.qgroups * kp.n_blocks;
+  ItemRec* items = ws.take<ItemRec>((size_t)n_items);
   const size_t lists = (size_t)n_queries * kp.n_blocks * k;
   float* part_d = ws.take<float>(lists);
   int* part_id = ws.take<int>(lists);
 
   NLSH_CUDA_TRY(cudaMemsetAsync(counter, 0, 64 * sizeof(int), st));
   const float* q_used = xq;
-  if (metric == NLSH_METRIC_ANGULAR || metric == NLSH_METRIC_COSINE) {
-    normalize_rows_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(
-        xq, n_queries, d, metric == NLSH_METRIC_ANGULAR ? 1e-8f : 0.f, qn);
+  const bool normalise = metric == NLSH_METRIC_ANGULAR || metric == NLSH_METRIC_COSINE;
+  if (normalise || (reinterpret_cast<uintptr_t>(xq) & 15) != 0) {
+    prepare_queries_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(
+        xq, n_queries, d, d, metric == NLSH_METRIC_ANGULAR ? 1 : (metric == NLSH_METRIC_COSINE ? 2 : 0), qn);
     NLSH_CUDA_TRY(nlsh_post_launch());
     q_used = qn;
   }
@@ -1044,6 +1203,7 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
   a.xs = xdb;
   a.ids = nullptr;
   a.q = q_used;
+  a.items = items;
   a.item_counter = counter;
   a.part_d = part_d;
   a.part_id = part_id;
@@ -1063,10 +1223,13 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
   a.d_pad = geom.d_pad;
   a.n_boxes = geom.n_boxes;
   a.bps = geom.bps;
+  a.nqb = geom.nqb;
   a.n_chunks = geom.n_chunks;
   a.stages = geom.stages;
   const int grid = nlsh_num_sms() * geom.ctas_per_sm;
   if (n_rows > 0) {
+    plan_items_kernel<<<nlsh_num_sms() * 4, 256, 0, st>>>(a, items, n_items);
+    NLSH_CUDA_TRY(nlsh_post_launch());
     int rc = launch_scan_metric(metric, a, geom, true, grid, st);
     if (rc != NLSH_OK) return rc;
   } else {
