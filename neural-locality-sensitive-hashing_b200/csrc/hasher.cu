@@ -177,6 +177,10 @@ __global__ void codes_kernel(const float* __restrict__ logits, long long n, int 
 
 // One warp per row: the p cheapest flip-masks (cost = sum of |logit| over flipped bits,
 // added in logit-index order; ties by smaller mask) XOR the hard code.
+// Only the min(p, hs) cheapest bits (ties: lower bit position first) can occur in one of the p
+// cheapest masks (each of those single-bit masks, and the empty mask, precedes any mask that
+// contains a costlier bit), so 2^min(p, hs) masks are enumerated instead of 2^hs; the result
+// is identical to the full enumeration of oracle.topp_probes.
 template <int KPL>
 __global__ void __launch_bounds__(128)
     probes_bernoulli_kernel(const float* __restrict__ logits, long long n, int hs, int head, int p,
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(128)
   if (row >= n) return;
   const int lane = lane_id();
   const float thr = head_threshold(head);
-  float a[NLSH_MAX_HASH_BITS];
+  float a[NLSH_MAX_HASH_BITS];  // a[i] = |logit i|; logit i is bit position hs - 1 - i
   int base = 0;
 #pragma unroll
   for (int i = 0; i < NLSH_MAX_HASH_BITS; ++i) {
@@ -196,17 +200,43 @@ __global__ void __launch_bounds__(128)
       base = (base << 1) | (v > thr ? 1 : 0);
     }
   }
+  // lane = bit position: rank of this bit among all bits by (cost, position)
+  float my_cost = 0.f;
+#pragma unroll
+  for (int i = 0; i < NLSH_MAX_HASH_BITS; ++i)
+    if (i < hs && lane == hs - 1 - i) my_cost = a[i];
+  int rank = 0;
+#pragma unroll
+  for (int i = 0; i < NLSH_MAX_HASH_BITS; ++i) {
+    if (i < hs) {
+      const int pos = hs - 1 - i;
+      rank += (a[i] < my_cost || (a[i] == my_cost && pos < lane)) ? 1 : 0;
+    }
+  }
+  const int n_sel = p < hs ? p : hs;
+  const unsigned sel = __ballot_sync(NLSH_FULL_MASK, lane < hs && rank < n_sel);  // selected positions
+
   WarpTopK<KPL, int> top;
   top.init(NLSH_ID_SENTINEL);
-  const int n_masks = 1 << hs;
+  const int n_masks = 1 << n_sel;
   for (int m0 = 0; m0 < n_masks; m0 += 32) {
-    const int m = m0 + lane;
+    const int mc = m0 + lane;  // compact mask over the selected bits (ascending position)
     float cost = 0.f;
+    int full = 0;
 #pragma unroll
     for (int i = 0; i < NLSH_MAX_HASH_BITS; ++i) {
-      if (i < hs && ((m >> (hs - 1 - i)) & 1)) cost = __fadd_rn(cost, a[i]);
+      if (i < hs) {
+        const int pos = hs - 1 - i;
+        if ((sel >> pos) & 1u) {
+          const int j = __popc(sel & ((1u << pos) - 1u));
+          if ((mc >> j) & 1) {
+            cost = __fadd_rn(cost, a[i]);
+            full |= 1 << pos;
+          }
+        }
+      }
     }
-    top.offer(cost, m, m < n_masks, p);
+    top.offer(cost, full, mc < n_masks, p);
   }
 #pragma unroll
   for (int j = 0; j < KPL; ++j) {

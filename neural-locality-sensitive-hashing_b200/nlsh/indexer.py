@@ -231,6 +231,12 @@ class Indexer:
                 result[i] = [v for v in result[i] if v >= 0]
         return result, ncand_host.tolist()
 
+    def capture_query(self, n_queries, k=10, hash_times=10):
+        """CUDA-graph capture of query_tensors for a fixed batch shape: returns a GraphedQuery
+        whose call replays hash -> probe selection -> scan + top-k (about a dozen launches) as
+        one graph launch."""
+        return GraphedQuery(self, n_queries, k, hash_times)
+
     @staticmethod
     def probes_from_sets(sets, device, width=None):
         """List[Set[int]] (e.g. the reference's hash() output) -> int32 [n, width] probes."""
@@ -240,3 +246,35 @@ class Indexer:
             vals = list(s)
             arr[i, :len(vals)] = vals
         return torch.from_numpy(arr).to(device)
+
+
+class GraphedQuery:
+    """`Indexer.query_tensors` for a fixed (n_queries, k, hash_times), captured once into a CUDA
+    graph and replayed per batch: no per-launch host cost, no allocations.  The graph reads the
+    hasher's live parameter tensors and the index arrays in place; build a new one after the
+    index is rebuilt.  Call with a CUDA (or pinned host) tensor [n_queries, d]; returns the
+    graph's static output tensors (ids int64 [Q, k], dists fp32 [Q, k], n_candidates int32 [Q]),
+    overwritten by the next call."""
+
+    def __init__(self, indexer, n_queries, k=10, hash_times=10):
+        dev = indexer._candidate_vectors_gpu.device
+        self.indexer = indexer
+        self.q = torch.zeros((n_queries, indexer._dim), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up off the capture stream (sizes the workspace)
+            for _ in range(2):
+                indexer.query_tensors(self.q, k, hash_times)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        launches0 = _native.kernel_launch_count()
+        with torch.cuda.graph(self.graph):
+            self.ids, self.dists, self.ncand = indexer.query_tensors(self.q, k, hash_times)
+        self.kernels_per_replay = _native.kernel_launch_count() - launches0
+        # the captured kernels hold raw pointers into the scratch buffer: keep it alive
+        self._keepalive = _native._workspaces.get((dev.type, dev.index))
+
+    def __call__(self, query_vectors):
+        self.q.copy_(query_vectors, non_blocking=True)
+        self.graph.replay()
+        return self.ids, self.dists, self.ncand

@@ -54,6 +54,28 @@ class ShardedIndexer:
         m_ids, m_d = _native.merge_topk(g_d, g_ids)
         return m_ids, m_d, ncand
 
+    def capture_query(self, n_queries, k=10, hash_times=10):
+        """The local search (hash -> scan + top-k) as one CUDA graph; the all-gather and the
+        merge of the shard lists stay eager launches behind it.  Returns a callable
+        query_vectors -> (ids, dists, n_candidates); `.kernels_per_call` counts this library's
+        kernels per call."""
+        graphed = self.local.capture_query(n_queries, k, hash_times)
+        multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+        def run(query_vectors):
+            ids, dists, ncand = graphed(query_vectors)
+            if not multi:
+                return ids, dists, ncand
+            g_ids, g_d = all_gather_topk(ids, dists, self.group)
+            total = ncand.clone()
+            dist.all_reduce(total, group=self.group)
+            m_ids, m_d = _native.merge_topk(g_d, g_ids)
+            return m_ids, m_d, total
+
+        run.kernels_per_call = graphed.kernels_per_replay + (1 if multi else 0)
+        run.graphed = graphed
+        return run
+
     def query(self, query_vectors, k=10, hash_times=10, probes=None):
         ids, _, ncand = self.query_tensors(query_vectors, k, hash_times, probes)
         rows = ids.cpu().tolist()

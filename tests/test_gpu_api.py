@@ -137,3 +137,25 @@ def test_full_size_properties_config2():
     assert (ncand == n).all()
     torch.testing.assert_close(dists, gt_d[:64], rtol=1e-5, atol=0)
     assert recall_at_k_tensors(gt[:64], ids) >= 0.999
+
+
+def test_graphed_query_equals_eager():
+    from encoders import MultiLayerRelu
+    from nlsh.hashings import MultivariateBernoulli
+    from nlsh.indexer import Indexer
+    torch.manual_seed(9)
+    X = mixture(50000, 64, 300, seed=31).cuda()
+    hashing = MultivariateBernoulli(MultiLayerRelu(64, [64, 64]), 7, None)
+    hashing.train_mode(False)
+    idx = Indexer(hashing, X, None, metric="l2")
+    graphed = idx.capture_query(777, k=10, hash_times=4)
+    assert graphed.kernels_per_replay >= 8
+    for seed in (1, 2, 3):
+        Q = mixture(777, 64, 300, seed=31 + seed).cuda()
+        e_ids, e_d, e_n = idx.query_tensors(Q, k=10, hash_times=4)
+        g_ids, g_d, g_n = graphed(Q)
+        assert torch.equal(e_ids, g_ids) and torch.equal(e_d, g_d) and torch.equal(e_n, g_n)
+    # pinned host input is copied into the graph's static buffer
+    Qh = mixture(777, 64, 300, seed=77).pin_memory()
+    g_ids, _, _ = graphed(Qh)
+    assert torch.equal(g_ids, idx.query_tensors(Qh.cuda(), k=10, hash_times=4)[0])
