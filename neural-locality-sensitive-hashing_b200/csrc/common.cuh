@@ -183,12 +183,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // try_wait suspends the thread in hardware for a bounded time; a pipeline that never
-  // completes traps (-> CUDA error on the host) instead of hanging the device.
-  uint32_t polls = 0;
+  // try_wait suspends the thread in hardware (up to the hint) and returns early when the phase
+  // completes.  A wait that lasts 4 s means the pipeline is broken: trap (-> CUDA error on the
+  // host) instead of hanging the device.
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls > (1u << 22)) __trap();
+    if (global_timer_ns() - t0 > 4000000000ull) __trap();
   }
 }
 // global -> shared bulk copy (SASS UBLKCP), completion counted in bytes on `bar`.

@@ -5,7 +5,18 @@
 // Round-1 kernel for the dense contraction: an fp32 register-tiled SIMT GEMM with the
 // bias + activation fused into its epilogue.  It is exact fp32 (sequential-K FMA), which
 // is what the 1e-5 logit tolerance needs; the tcgen05 3xTF32 version replaces it next.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
+
+// tensor-core path (tc_linear.cu)
+bool nlsh_tc_layer_supported(int in_dim, int out_dim);
+int nlsh_tc_split(const float* x, size_t n, float* hi, float* lo, cudaStream_t st);
+int nlsh_tc_linear(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo,
+                   const float* bias, int M, int N, int K, int act, float act_scale, float* out_hi,
+                   float* out_lo, float* out_full, int ld_out, int* codes_out, int head,
+                   cudaStream_t st);
 
 namespace {
 
@@ -333,6 +344,92 @@ int launch_linear(const float* A, int lda, const nlsh_layer_t& L, float* C, int 
   return nlsh_check_cuda(nlsh_post_launch(), "linear_act_kernel launch");
 }
 
+// ---- tensor-core path (tcgen05, 3xTF32 split) ------------------------------------------------
+// NLSH_MLP_IMPL=simt forces the fp32 SIMT kernels (A/B runs); the default is the tensor cores
+// whenever every layer has in_dim % 4 == 0 and out_dim <= 256.
+bool mlp_use_tc(const nlsh_layer_t* layers, int32_t n_layers) {
+  const char* env = getenv("NLSH_MLP_IMPL");
+  if (env != nullptr && strcmp(env, "simt") == 0) return false;
+  for (int l = 0; l < n_layers; ++l)
+    if (!nlsh_tc_layer_supported(layers[l].in_dim, layers[l].out_dim)) return false;
+  return true;
+}
+
+struct TcPlan {
+  int64_t chunk;
+  size_t act_floats;     // per activation buffer: chunk * widest layer input
+  size_t weight_floats;  // all layers
+  int hs;
+};
+
+TcPlan tc_plan(int64_t n, const nlsh_layer_t* layers, int32_t n_layers) {
+  TcPlan p;
+  int width = 4;
+  p.weight_floats = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    if (layers[l].in_dim > width) width = layers[l].in_dim;
+    p.weight_floats += (size_t)layers[l].in_dim * layers[l].out_dim;
+  }
+  int64_t chunk = width > 512 ? 16384 : kMlpChunkRows;
+  if (n < chunk) chunk = n > 0 ? n : 1;
+  p.chunk = chunk;
+  p.act_floats = (size_t)chunk * width;
+  p.hs = layers[n_layers - 1].out_dim;
+  return p;
+}
+
+size_t tc_workspace_bytes(int64_t n, const nlsh_layer_t* layers, int32_t n_layers) {
+  const TcPlan p = tc_plan(n, layers, n_layers);
+  WorkspaceCarver ws(nullptr);
+  ws.take<float>(p.weight_floats);
+  ws.take<float>(p.weight_floats);
+  for (int i = 0; i < 4; ++i) ws.take<float>(p.act_floats);
+  ws.take<float>((size_t)p.chunk * p.hs);
+  return ws.total();
+}
+
+int mlp_hash_tc(const float* x, int64_t n, int32_t d, const nlsh_layer_t* layers, int32_t n_layers,
+                int32_t head, float* logits_out, int32_t* codes_out, void* workspace,
+                cudaStream_t st) {
+  const TcPlan p = tc_plan(n, layers, n_layers);
+  WorkspaceCarver ws(workspace);
+  float* w_hi = ws.take<float>(p.weight_floats);
+  float* w_lo = ws.take<float>(p.weight_floats);
+  float* act[4];
+  for (int i = 0; i < 4; ++i) act[i] = ws.take<float>(p.act_floats);
+  float* logits_tmp = ws.take<float>((size_t)p.chunk * p.hs);
+
+  // weights change between index builds while training: split them at every call (tiny)
+  size_t w_off[NLSH_MAX_LAYERS];
+  size_t off = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    w_off[l] = off;
+    const size_t cnt = (size_t)layers[l].in_dim * layers[l].out_dim;
+    int rc = nlsh_tc_split(layers[l].weight, cnt, w_hi + off, w_lo + off, st);
+    if (rc != NLSH_OK) return rc;
+    off += cnt;
+  }
+  for (int64_t r0 = 0; r0 < n; r0 += p.chunk) {
+    const int rows = (int)((n - r0) < p.chunk ? (n - r0) : p.chunk);
+    int rc = nlsh_tc_split(x + (size_t)r0 * d, (size_t)rows * d, act[0], act[1], st);
+    if (rc != NLSH_OK) return rc;
+    int cur = 0;  // act[cur], act[cur + 1] hold the split input of the next layer
+    float* logits_chunk = logits_out ? logits_out + (size_t)r0 * p.hs : logits_tmp;
+    for (int l = 0; l < n_layers; ++l) {
+      const bool last = (l == n_layers - 1);
+      const int nxt = cur ^ 2;
+      rc = nlsh_tc_linear(act[cur], act[cur + 1], w_hi + w_off[l], w_lo + w_off[l], layers[l].bias,
+                          rows, layers[l].out_dim, layers[l].in_dim, layers[l].act,
+                          layers[l].act_scale, last ? nullptr : act[nxt], last ? nullptr : act[nxt + 1],
+                          last ? logits_chunk : nullptr, layers[l].out_dim,
+                          last && codes_out ? codes_out + r0 : nullptr, head, st);
+      if (rc != NLSH_OK) return rc;
+      cur = nxt;
+    }
+  }
+  return NLSH_OK;
+}
+
 }  // namespace
 
 extern "C" size_t nlsh_mlp_workspace_bytes(int64_t n, const nlsh_layer_t* layers, int32_t n_layers) {
@@ -342,7 +439,12 @@ extern "C" size_t nlsh_mlp_workspace_bytes(int64_t n, const nlsh_layer_t* layers
   ws.take<float>(p.buf_floats);
   ws.take<float>(p.buf_floats);
   ws.take<float>((size_t)p.chunk * layers[n_layers - 1].out_dim);
-  return ws.total();
+  size_t need = ws.total();
+  if (mlp_use_tc(layers, n_layers)) {
+    const size_t tc = tc_workspace_bytes(n, layers, n_layers);
+    if (tc > need) need = tc;
+  }
+  return need;
 }
 
 extern "C" int nlsh_codes_from_logits(const float* logits, int64_t n, int32_t hash_size,
@@ -376,6 +478,9 @@ extern "C" int nlsh_mlp_hash_f32(const float* x, int64_t n, int32_t d, const nls
     nlsh_set_error("mlp: workspace %zu bytes < required %zu", workspace_bytes, need);
     return NLSH_ERR_WORKSPACE;
   }
+  if (mlp_use_tc(layers, n_layers) && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+    return mlp_hash_tc(x, n, d, layers, n_layers, head, logits_out, codes_out, workspace,
+                       static_cast<cudaStream_t>(stream));
   const MlpPlan plan = mlp_plan(n, layers, n_layers);
   const int hs = layers[n_layers - 1].out_dim;
   WorkspaceCarver ws(workspace);

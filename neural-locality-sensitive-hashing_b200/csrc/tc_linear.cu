@@ -1,0 +1,365 @@
+// Tensor-core path of the hasher's dense contraction (encoders.py:41-55 nn.Linear chains,
+// nlsh/hashings.py:19-22 output layer): C[M, N] = act(A[M, K] W[N, K]^T + b) on the 5th-gen
+// tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM) at fp32-equivalent accuracy.
+//
+// Accuracy: a tf32 operand keeps 11 significant bits, far from the 1e-5 logit bar, so every
+// fp32 operand x is split exactly into hi = x with the 13 low mantissa bits cleared and
+// lo = x - hi, and each product is issued three times into the same fp32 accumulator:
+// hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-22 relative).  The split operands are
+// materialised in global memory (weights once per call; activations by the previous layer's
+// epilogue, so a chunk's hi/lo activations stay L2 resident) and streamed by TMA.
+//
+// One CTA = one 128-row tile of A against all N <= 256 columns.  Warp roles: warp 4 lane 0
+// issues the TMA loads (SWIZZLE_128B, K-major, 32 fp32 = 128 bytes per row per K block) into
+// a ring of stages; warp 5 lane 0 issues the tcgen05.mma's and commits stage releases /
+// accumulator completion to mbarriers; warps 0-3 are the epilogue: tcgen05.ld the 128 x N
+// accumulator (one row per thread), add bias, apply the activation, and either write the
+// next layer's hi/lo operands or the logits + bucket codes.
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTcBM = 128;      // rows per CTA = UMMA M
+constexpr int kTcBK = 32;       // fp32 per K block: 128 bytes = one SWIZZLE_128B row
+constexpr int kTcThreads = 192;
+
+struct TcArgs {
+  const float* bias;  // [N] or nullptr
+  float* out_hi;      // [M, ld_out] split outputs for the next layer (nullptr on the last)
+  float* out_lo;
+  float* out_full;    // [M, ld_out] plain fp32 output (logits), may be nullptr
+  int* codes_out;     // [M] bucket codes (last layer), may be nullptr
+  int M, N, K;
+  int n_pad;          // UMMA N: N rounded up to a multiple of 16
+  int ld_out;
+  int act;
+  float act_scale;
+  int head;
+  int stages;
+  int tmem_cols;      // power of two >= max(32, n_pad)
+};
+
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4 in bits [0,14), LBO = 1 (unused for swizzled K-major) in [16,30),
+// SBO = 1024 bytes (one 8-row swizzle atom) >> 4 in [32,46), version 1 in [46,48),
+// layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem_ptr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem_ptr) >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, tf32 A and B, both
+// K-major, N >> 3 in bits [17,23), M >> 4 in bits [24,29).
+__device__ __forceinline__ uint32_t make_tf32_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// All tcgen05 operations issued so far by this thread arrive on `bar` when they complete.
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+// 16 consecutive accumulator columns of this thread's TMEM lane.
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tc_act(float v, int act, float scale) {
+  if (act == NLSH_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == NLSH_ACT_SIN) return sinf(scale * v);
+  return v;
+}
+
+__device__ __forceinline__ float tf32_hi(float x) {
+  return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+    tc_linear_kernel(const TcArgs a, const __grid_constant__ CUtensorMap map_a_hi,
+                     const __grid_constant__ CUtensorMap map_a_lo,
+                     const __grid_constant__ CUtensorMap map_w_hi,
+                     const __grid_constant__ CUtensorMap map_w_lo) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  const size_t a_bytes = (size_t)kTcBM * kTcBK * sizeof(float);    // 16 KB
+  const size_t w_bytes = (size_t)a.n_pad * kTcBK * sizeof(float);  // n_pad * 128 B (multiple of 2 KB)
+  const size_t stage_bytes = 2 * a_bytes + 2 * w_bytes;
+  unsigned char* tail = base + (size_t)a.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);  // [stages <= 4]
+  uint64_t* empty_bar = full_bar + 4;                      // [stages <= 4]
+  uint64_t* acc_bar = empty_bar + 4;                       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int m0 = blockIdx.x * kTcBM;
+  const int n_kblocks = (a.K + kTcBK - 1) / kTcBK;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) {  // one warp allocates the accumulator columns and owns the deallocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------- TMA producer ---------------------------------------
+    if (lane == 0) {
+      for (int kb = 0; kb < n_kblocks; ++kb) {
+        const int s = kb % a.stages;
+        mbar_wait(&empty_bar[s], (((unsigned)kb / (unsigned)a.stages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], (unsigned)stage_bytes);
+        unsigned char* st = base + (size_t)s * stage_bytes;
+        tma_load_2d(st, &map_a_hi, kb * kTcBK, m0, &full_bar[s]);
+        tma_load_2d(st + a_bytes, &map_a_lo, kb * kTcBK, m0, &full_bar[s]);
+        tma_load_2d(st + 2 * a_bytes, &map_w_hi, kb * kTcBK, 0, &full_bar[s]);
+        tma_load_2d(st + 2 * a_bytes + w_bytes, &map_w_lo, kb * kTcBK, 0, &full_bar[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ------------------------------- MMA issuer -----------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_tf32_idesc(a.n_pad);
+      for (int kb = 0; kb < n_kblocks; ++kb) {
+        const int s = kb % a.stages;
+        mbar_wait(&full_bar[s], ((unsigned)kb / (unsigned)a.stages) & 1u);
+        tc_fence_after();
+        unsigned char* st = base + (size_t)s * stage_bytes;
+        const uint64_t da_hi = make_kmajor_sw128_desc(st);
+        const uint64_t da_lo = make_kmajor_sw128_desc(st + a_bytes);
+        const uint64_t dw_hi = make_kmajor_sw128_desc(st + 2 * a_bytes);
+        const uint64_t dw_lo = make_kmajor_sw128_desc(st + 2 * a_bytes + w_bytes);
+#pragma unroll
+        for (int k = 0; k < kTcBK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes: +2 in (addr >> 4)
+          const uint64_t adv = (uint64_t)(k * 2);
+          tc_mma_tf32(tmem_base, da_hi + adv, dw_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_mma_tf32(tmem_base, da_hi + adv, dw_lo + adv, idesc, 1u);
+          tc_mma_tf32(tmem_base, da_lo + adv, dw_hi + adv, idesc, 1u);
+        }
+        tc_commit(&empty_bar[s]);  // the stage may be refilled once these MMAs have read it
+      }
+      tc_commit(acc_bar);  // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------- epilogue (warps 0-3) -------------------------------
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int row = m0 + warp * 32 + lane;  // TMEM lane = accumulator row
+    const bool row_ok = row < a.M;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool last = a.out_hi == nullptr;
+    const float thr = a.head == NLSH_HEAD_TANH ? 5.9604644775390625e-08f : 8.940696716308594e-08f;
+    int code = 0;
+    float best = 0.f;
+    for (int c0 = 0; c0 < a.n_pad; c0 += 16) {
+      float v[16];
+      tc_ld16(lane_addr + (uint32_t)c0, v);  // warp-collective: every lane takes part
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int col = c0 + i;
+        float x = v[i] + ((a.bias != nullptr && col < a.N) ? a.bias[col] : 0.f);
+        v[i] = tc_act(x, a.act, a.act_scale);
+      }
+      if (!row_ok) continue;
+      if (!last) {
+        float* ph = a.out_hi + (size_t)row * a.ld_out + c0;
+        float* pl = a.out_lo + (size_t)row * a.ld_out + c0;
+        if (c0 + 16 <= a.N && (a.ld_out & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 h, l;
+            h.x = tf32_hi(v[i + 0]); l.x = v[i + 0] - h.x;
+            h.y = tf32_hi(v[i + 1]); l.y = v[i + 1] - h.y;
+            h.z = tf32_hi(v[i + 2]); l.z = v[i + 2] - h.z;
+            h.w = tf32_hi(v[i + 3]); l.w = v[i + 3] - h.w;
+            *reinterpret_cast<float4*>(ph + i) = h;
+            *reinterpret_cast<float4*>(pl + i) = l;
+          }
+        } else {
+          for (int i = 0; i < 16 && c0 + i < a.N; ++i) {
+            const float h = tf32_hi(v[i]);
+            ph[i] = h;
+            pl[i] = v[i] - h;
+          }
+        }
+      } else {
+        for (int i = 0; i < 16 && c0 + i < a.N; ++i) {
+          const int col = c0 + i;
+          if (a.out_full) a.out_full[(size_t)row * a.ld_out + col] = v[i];
+          if (a.head == NLSH_HEAD_SOFTMAX) {
+            if (col == 0 || v[i] > best) {
+              best = v[i];
+              code = col;
+            }
+          } else {
+            code = (code << 1) | (v[i] > thr ? 1 : 0);  // MSB first (utils.pyx:12-14)
+          }
+        }
+      }
+    }
+    if (last && row_ok && a.codes_out) a.codes_out[row] = code;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+  }
+}
+
+// x -> (hi, lo): hi = x with the 13 low mantissa bits cleared (a tf32 value), lo = x - hi (exact).
+__global__ void split_tf32_kernel(const float* __restrict__ x, size_t n, float* __restrict__ hi,
+                                  float* __restrict__ lo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = i; j < n; j += stride) {
+    const float v = x[j];
+    const float h = tf32_hi(v);
+    hi[j] = h;
+    lo[j] = v - h;
+  }
+}
+
+typedef CUresult (*TcEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int tc_make_map(CUtensorMap* map, const float* base, long long rows, int cols, int box_rows) {
+  static TcEncodeTiledFn encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    NLSH_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      nlsh_set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return NLSH_ERR_CUDA;
+    }
+    encode = reinterpret_cast<TcEncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)(rows > 0 ? rows : 1)};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims,
+                            strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    nlsh_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%d box_rows=%d)",
+                   (int)r, rows, cols, box_rows);
+    return NLSH_ERR_CUDA;
+  }
+  return NLSH_OK;
+}
+
+}  // namespace
+
+// ---- interface used by hasher.cu ---------------------------------------------------------
+bool nlsh_tc_layer_supported(int in_dim, int out_dim) {
+  return in_dim % 4 == 0 && in_dim >= 4 && out_dim >= 1 && out_dim <= 256;
+}
+
+int nlsh_tc_split(const float* x, size_t n, float* hi, float* lo, cudaStream_t st) {
+  if (n == 0) return NLSH_OK;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_tf32_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, hi, lo);
+  return nlsh_check_cuda(nlsh_post_launch(), "split_tf32_kernel launch");
+}
+
+// One layer on the tensor cores.  a_hi / a_lo: [M, K] split input; w_hi / w_lo: [N, K] split
+// weights; outputs as in TcArgs.
+int nlsh_tc_linear(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo,
+                   const float* bias, int M, int N, int K, int act, float act_scale, float* out_hi,
+                   float* out_lo, float* out_full, int ld_out, int* codes_out, int head,
+                   cudaStream_t st) {
+  TcArgs a{};
+  a.bias = bias;
+  a.out_hi = out_hi;
+  a.out_lo = out_lo;
+  a.out_full = out_full;
+  a.codes_out = codes_out;
+  a.M = M;
+  a.N = N;
+  a.K = K;
+  a.n_pad = (N + 15) / 16 * 16;
+  a.ld_out = ld_out;
+  a.act = act;
+  a.act_scale = act_scale;
+  a.head = head;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < a.n_pad) a.tmem_cols *= 2;
+  const size_t stage_bytes =
+      2 * (size_t)kTcBM * kTcBK * sizeof(float) + 2 * (size_t)a.n_pad * kTcBK * sizeof(float);
+  a.stages = 4;
+  while (a.stages > 1 && a.stages * stage_bytes + 2048 > 220 * 1024) --a.stages;
+  const size_t smem = a.stages * stage_bytes + 2048;
+
+  CUtensorMap m_a_hi, m_a_lo, m_w_hi, m_w_lo;
+  int rc;
+  if ((rc = tc_make_map(&m_a_hi, a_hi, M, K, kTcBM)) != NLSH_OK) return rc;
+  if ((rc = tc_make_map(&m_a_lo, a_lo, M, K, kTcBM)) != NLSH_OK) return rc;
+  if ((rc = tc_make_map(&m_w_hi, w_hi, N, K, a.n_pad)) != NLSH_OK) return rc;
+  if ((rc = tc_make_map(&m_w_lo, w_lo, N, K, a.n_pad)) != NLSH_OK) return rc;
+  NLSH_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  const unsigned grid = (unsigned)((M + kTcBM - 1) / kTcBM);
+  tc_linear_kernel<<<grid, kTcThreads, smem, st>>>(a, m_a_hi, m_a_lo, m_w_hi, m_w_lo);
+  return nlsh_check_cuda(nlsh_post_launch(), "tc_linear_kernel launch");
+}
