@@ -5,7 +5,11 @@
 // Accuracy: a tf32 operand keeps 11 significant bits, far from the 1e-5 logit bar, so every
 // fp32 operand x is split exactly into hi = x with the 13 low mantissa bits cleared and
 // lo = x - hi, and each product is issued three times into the same fp32 accumulator:
-// hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-22 relative).  The split operands are
+// hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-22 relative).  The tensor core truncates
+// when it adds into the fp32 accumulator, a one-sided error that grows with the number of
+// accumulation steps, so the large hi*hi term is spread round-robin over up to four TMEM
+// accumulators and the two small cross terms go to their own accumulator; the epilogue adds
+// them with ordinary round-to-nearest fp32 adds.  The split operands are
 // materialised in global memory (weights once per call; activations by the previous layer's
 // epilogue, so a chunk's hi/lo activations stay L2 resident) and streamed by TMA.
 //
@@ -39,7 +43,8 @@ struct TcArgs {
   float act_scale;
   int head;
   int stages;
-  int tmem_cols;      // power of two >= max(32, n_pad)
+  int n_main;         // TMEM accumulators for hi*hi (k-block kb uses kb % n_main); one more for the cross terms
+  int tmem_cols;      // power of two >= max(32, (n_main + 1) * n_pad)
 };
 
 __device__ __forceinline__ void tc_fence_before() {
@@ -181,12 +186,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const uint64_t da_lo = make_kmajor_sw128_desc(st + a_bytes);
         const uint64_t dw_hi = make_kmajor_sw128_desc(st + 2 * a_bytes);
         const uint64_t dw_lo = make_kmajor_sw128_desc(st + 2 * a_bytes + w_bytes);
+        const uint32_t acc_main = tmem_base + (uint32_t)((kb % a.n_main) * a.n_pad);
+        const uint32_t acc_cross = tmem_base + (uint32_t)(a.n_main * a.n_pad);
 #pragma unroll
         for (int k = 0; k < kTcBK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes: +2 in (addr >> 4)
           const uint64_t adv = (uint64_t)(k * 2);
-          tc_mma_tf32(tmem_base, da_hi + adv, dw_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_mma_tf32(tmem_base, da_hi + adv, dw_lo + adv, idesc, 1u);
-          tc_mma_tf32(tmem_base, da_lo + adv, dw_hi + adv, idesc, 1u);
+          tc_mma_tf32(acc_main, da_hi + adv, dw_hi + adv, idesc, (kb >= a.n_main || k > 0) ? 1u : 0u);
+          tc_mma_tf32(acc_cross, da_hi + adv, dw_lo + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_mma_tf32(acc_cross, da_lo + adv, dw_hi + adv, idesc, 1u);
         }
         tc_commit(&empty_bar[s]);  // the stage may be refilled once these MMAs have read it
       }
@@ -204,9 +211,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const float thr = a.head == NLSH_HEAD_TANH ? 5.9604644775390625e-08f : 8.940696716308594e-08f;
     int code = 0;
     float best = 0.f;
+    const int n_main_used = a.n_main < n_kblocks ? a.n_main : n_kblocks;
     for (int c0 = 0; c0 < a.n_pad; c0 += 16) {
-      float v[16];
+      float v[16], t[16];
       tc_ld16(lane_addr + (uint32_t)c0, v);  // warp-collective: every lane takes part
+      for (int j = 1; j < n_main_used; ++j) {
+        tc_ld16(lane_addr + (uint32_t)(j * a.n_pad + c0), t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += t[i];
+      }
+      tc_ld16(lane_addr + (uint32_t)(a.n_main * a.n_pad + c0), t);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += t[i];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int col = c0 + i;
@@ -343,8 +359,11 @@ int nlsh_tc_linear(const float* a_hi, const float* a_lo, const float* w_hi, cons
   a.act = act;
   a.act_scale = act_scale;
   a.head = head;
+  a.n_main = 512 / a.n_pad - 1;
+  if (a.n_main > 4) a.n_main = 4;
+  if (a.n_main < 1) a.n_main = 1;
   a.tmem_cols = 32;
-  while (a.tmem_cols < a.n_pad) a.tmem_cols *= 2;
+  while (a.tmem_cols < (a.n_main + 1) * a.n_pad) a.tmem_cols *= 2;
   const size_t stage_bytes =
       2 * (size_t)kTcBM * kTcBK * sizeof(float) + 2 * (size_t)a.n_pad * kTcBK * sizeof(float);
   a.stages = 4;

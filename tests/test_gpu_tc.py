@@ -15,7 +15,7 @@ def run_mlp(x, weights, biases, head=0):
     return _native.mlp_hash(x, layers, head)
 
 
-@pytest.mark.parametrize("m,dims", [(128, [32, 16]), (1, [128, 256, 256, 12]), (300, [64, 256]),
+@pytest.mark.parametrize("m,dims", [(128, [32, 12]), (1, [128, 256, 256, 12]), (300, [64, 256, 15]),
                                     (5000, [128, 256, 256, 12]), (40000, [100, 256, 256, 10]),
                                     (1000, [960, 256, 256, 9]), (777, [128, 64, 64, 8]), (129, [36, 100, 4])])
 def test_tc_path_matches_fp64_and_simt(m, dims):
