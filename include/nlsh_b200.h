@@ -173,11 +173,15 @@ int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const float* xdb, in
 
 /* ---------------------------------------------------------------------------------------
  * Merge of G per-shard top-k lists (after the NCCL all-gather of the sharded search; the
- * reference has no multi-GPU path).  dists [G, n_queries, k] ascending per list, ids
- * [G, n_queries, k] (-1 = empty).  Output as nlsh_query_scan_topk.
+ * reference has no multi-GPU path).  List l lives at dists + l * dist_stride / ids +
+ * l * id_stride (strides in elements; 0 = contiguous [G, n_queries, k]), [n_queries, k] each,
+ * ascending, ids < 0 = empty slot - so the lists can be read in place from the packed
+ * all-gather buffer.  ncand (optional, with ncand_out): per-shard candidate counts
+ * [G][n_queries] at stride ncand_stride, summed into ncand_out.  Output as nlsh_query_scan_topk.
  * ------------------------------------------------------------------------------------- */
-int nlsh_merge_topk(const float* dists, const int64_t* ids, int32_t n_lists, int64_t n_queries,
-                    int32_t k, int64_t* ids_out, float* dists_out, void* stream);
+int nlsh_merge_topk(const float* dists, const int64_t* ids, int64_t dist_stride, int64_t id_stride,
+                    const int32_t* ncand, int64_t ncand_stride, int32_t n_lists, int64_t n_queries,
+                    int32_t k, int64_t* ids_out, float* dists_out, int32_t* ncand_out, void* stream);
 
 /* recall@k on device: mean over queries of |gt[q,:k_gt] ∩ pred[q,:k_pred]| / k_gt, the
  * definition of nlsh/metrics.py:4-25 (negative pred ids never match). hits_out: device

@@ -138,6 +138,43 @@ struct WarpTopK {
     }
   }
 
+  // Replace the (empty) list by the sorted set of one candidate per lane: a 32-wide bitonic
+  // sort over the lanes costs about four insert()s, where feeding the same 32 candidates
+  // through offer() into an empty list costs k + k ln(32 / k) of them.
+  __device__ __forceinline__ void seed32(float cd, IdT cid, bool valid, IdT sentinel, int k) {
+    const int lane = lane_id();
+    float sd = valid ? cd : __int_as_float(0x7f800000);
+    IdT si = valid ? cid : sentinel;
+    if (sd != sd) {  // NaN never enters a list
+      sd = __int_as_float(0x7f800000);
+      si = sentinel;
+    }
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const float od = __shfl_xor_sync(NLSH_FULL_MASK, sd, stride);
+        const IdT oi = __shfl_xor_sync(NLSH_FULL_MASK, si, stride);
+        const bool up = (lane & size) == 0;          // ascending block?
+        const bool lower = (lane & stride) == 0;     // this lane holds the lower index of the pair
+        const bool other_less = lex_less<IdT>(od, oi, sd, si);
+        // the lower lane of an ascending pair keeps the minimum, etc.
+        if (other_less == (up == lower)) {
+          sd = od;
+          si = oi;
+        }
+      }
+    }
+    d[0] = sd;
+    id[0] = si;
+#pragma unroll
+    for (int j = 1; j < KPL; ++j) {
+      d[j] = __int_as_float(0x7f800000);
+      id[j] = sentinel;
+    }
+    refresh_tau(k);
+  }
+
   // Element at position pos (warp-uniform pos) broadcast to all lanes.
   __device__ __forceinline__ void get(int pos, float& od, IdT& oi) const {
     const int slot = pos >> 5;

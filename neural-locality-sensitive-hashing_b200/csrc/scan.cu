@@ -362,17 +362,21 @@ struct ItemLists {
   // Row tile epilogue: scores of the 128 rows x ng queries go through shared memory to the
   // warp that owns each query's list (buffers double-buffered on `parity`: one named barrier
   // per tile is enough).
+  // `first` = first tile of the item (lists still empty): its first 32 rows seed the list with
+  // one bitonic sort instead of k + k ln(32/k) inserts.
   template <int METRIC>
   __device__ __forceinline__ void tile_epilogue(const Acc& acc, float* score_s, int* id_s, int parity,
                                                 int r_local, int cand_id, bool valid, int ng,
-                                                int warp, int lane, int k) {
+                                                int warp, int lane, int k, bool first) {
     float* sc = score_s + parity * (kG * kTileRows);
     int* idb = id_s + parity * kTileRows;
-    const float xx = acc.sum_xx();
     idb[r_local] = valid ? cand_id : NLSH_ID_SENTINEL;
+    if (valid) {
+      const float xx = acc.sum_xx();
 #pragma unroll
-    for (int g = 0; g < kG; ++g)
-      if (g < ng) sc[g * kTileRows + r_local] = finalize_distance<METRIC>(acc.sum(g), xx);
+      for (int g = 0; g < kG; ++g)
+        if (g < ng) sc[g * kTileRows + r_local] = finalize_distance<METRIC>(acc.sum(g), xx);
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory");
 #pragma unroll
     for (int i = 0; i < kListsPerWarp; ++i) {
@@ -382,7 +386,12 @@ struct ItemLists {
         for (int j = 0; j < kTileRows / 32; ++j) {
           const int r = lane + 32 * j;
           const int cid = idb[r];
-          top[i].offer(sc[g * kTileRows + r], cid, cid != NLSH_ID_SENTINEL && cid != self_id[i], k);
+          const bool ok = cid != NLSH_ID_SENTINEL && cid != self_id[i];
+          const float cd = ok ? sc[g * kTileRows + r] : 0.f;
+          if (first && j == 0)
+            top[i].seed32(cd, cid, ok, NLSH_ID_SENTINEL, k);
+          else
+            top[i].offer(cd, cid, ok, k);
         }
       }
     }
@@ -529,6 +538,7 @@ __global__ void __launch_bounds__(32 * (kConsumerWarps + 1), KPL <= 2 ? 3 : 2)
     for (int t = 0; t < n_tiles; ++t) {
       const int row = row0 + t * kTileRows + r_local;
       const bool valid = row < row1;
+      const bool warp_has_rows = row0 + t * kTileRows + warp * 32 < row1;
       int cand_id = NLSH_ID_SENTINEL;
       if (valid) cand_id = a.ids ? a.ids[row] : row;  // latency hidden behind the chunk loop
       Acc acc;
@@ -538,13 +548,14 @@ __global__ void __launch_bounds__(32 * (kConsumerWarps + 1), KPL <= 2 ? 3 : 2)
         const int nb = (a.n_boxes - box0) < a.bps ? (a.n_boxes - box0) : a.bps;
         const int s = (int)(ring % (unsigned)a.stages);
         mbar_wait(&full_bar[s], (ring / (unsigned)a.stages) & 1u);
-        consume_stage<METRIC>(a, acc, stage_buf + s * stage_floats, box0, nb, r_local, xr, qs, ng);
+        if (warp_has_rows)  // a warp whose 32 rows all lie past the chunk end only keeps the ring in step
+          consume_stage<METRIC>(a, acc, stage_buf + s * stage_floats, box0, nb, r_local, xr, qs, ng);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
         ++ring;
       }
       lists.template tile_epilogue<METRIC>(acc, score_s, id_s, (int)(tcount & 1u), r_local, cand_id,
-                                           valid, ng, warp, lane, a.k);
+                                           valid, ng, warp, lane, a.k, t == 0);
       ++tcount;
     }
     lists.write_out(a, rec->f, ng, rec->chunk, warp, lane);
@@ -626,7 +637,7 @@ __global__ void __launch_bounds__(32 * kConsumerWarps, 2) scan_kernel_sync(const
         __syncthreads();
       }
       lists.template tile_epilogue<METRIC>(acc, score_s, id_s, (int)(tcount & 1u), r_local, cand_id,
-                                           valid, ng, warp, lane, a.k);
+                                           valid, ng, warp, lane, a.k, t == 0);
       ++tcount;
     }
     lists.write_out(a, rec->f, ng, rec->chunk, warp, lane);
@@ -819,27 +830,33 @@ __global__ void __launch_bounds__(128)
 template <int KPL>
 __global__ void __launch_bounds__(128)
     merge_lists_kernel(const float* __restrict__ dists, const long long* __restrict__ ids,
-                       int n_lists, long long n_queries, int k, long long* __restrict__ ids_out,
-                       float* __restrict__ dists_out) {
+                       long long dist_stride, long long id_stride, const int* __restrict__ ncand,
+                       long long ncand_stride, int n_lists, long long n_queries, int k,
+                       long long* __restrict__ ids_out, float* __restrict__ dists_out,
+                       int* __restrict__ ncand_out) {
   const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= n_queries) return;
   const int lane = lane_id();
   const long long sentinel = 0x7fffffffffffffffll;
   WarpTopK<KPL, long long> top;
   top.init(sentinel);
+  int total = 0;
   for (int l = 0; l < n_lists; ++l) {
-    const size_t base = ((size_t)l * n_queries + q) * k;
+    const float* dl = dists + (size_t)l * dist_stride + (size_t)q * k;
+    const long long* il = ids + (size_t)l * id_stride + (size_t)q * k;
+    if (ncand) total += ncand[(size_t)l * ncand_stride + q];
     for (int e0 = 0; e0 < k; e0 += 32) {
       const int e = e0 + lane;
       float cd = 0.f;
       long long cid = -1;
       if (e < k) {
-        cd = dists[base + e];
-        cid = ids[base + e];
+        cd = dl[e];
+        cid = il[e];
       }
       top.offer(cd, cid, cid >= 0, k);
     }
   }
+  if (lane == 0 && ncand_out) ncand_out[q] = total;
 #pragma unroll
   for (int j = 0; j < KPL; ++j) {
     const int pos = j * 32 + lane;
@@ -1242,24 +1259,32 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
                                dists_out, nullptr, st);
 }
 
-extern "C" int nlsh_merge_topk(const float* dists, const int64_t* ids, int32_t n_lists,
-                               int64_t n_queries, int32_t k, int64_t* ids_out, float* dists_out,
-                               void* stream) {
+extern "C" int nlsh_merge_topk(const float* dists, const int64_t* ids, int64_t dist_stride,
+                               int64_t id_stride, const int32_t* ncand, int64_t ncand_stride,
+                               int32_t n_lists, int64_t n_queries, int32_t k, int64_t* ids_out,
+                               float* dists_out, int32_t* ncand_out, void* stream) {
   NLSH_REQUIRE(n_lists >= 1 && n_queries >= 0, "merge: bad shape n_lists=%d n_queries=%lld", n_lists,
                (long long)n_queries);
   NLSH_REQUIRE(k >= 1 && k <= NLSH_MAX_K, "merge: k=%d outside [1, %d]", k, NLSH_MAX_K);
   if (n_queries == 0) return NLSH_OK;
   NLSH_REQUIRE(dists && ids && ids_out && dists_out, "merge: null pointer");
+  NLSH_REQUIRE((ncand == nullptr) == (ncand_out == nullptr), "merge: ncand and ncand_out go together");
+  if (dist_stride == 0) dist_stride = n_queries * k;
+  if (id_stride == 0) id_stride = n_queries * k;
+  if (ncand_stride == 0) ncand_stride = n_queries;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned blocks = (unsigned)((n_queries + 3) / 4);
   const long long* ids_ll = reinterpret_cast<const long long*>(ids);
   long long* out_ll = reinterpret_cast<long long*>(ids_out);
   if (k <= 32)
-    merge_lists_kernel<1><<<blocks, 128, 0, st>>>(dists, ids_ll, n_lists, n_queries, k, out_ll, dists_out);
+    merge_lists_kernel<1><<<blocks, 128, 0, st>>>(dists, ids_ll, dist_stride, id_stride, ncand, ncand_stride,
+                                                  n_lists, n_queries, k, out_ll, dists_out, ncand_out);
   else if (k <= 64)
-    merge_lists_kernel<2><<<blocks, 128, 0, st>>>(dists, ids_ll, n_lists, n_queries, k, out_ll, dists_out);
+    merge_lists_kernel<2><<<blocks, 128, 0, st>>>(dists, ids_ll, dist_stride, id_stride, ncand, ncand_stride,
+                                                  n_lists, n_queries, k, out_ll, dists_out, ncand_out);
   else
-    merge_lists_kernel<4><<<blocks, 128, 0, st>>>(dists, ids_ll, n_lists, n_queries, k, out_ll, dists_out);
+    merge_lists_kernel<4><<<blocks, 128, 0, st>>>(dists, ids_ll, dist_stride, id_stride, ncand, ncand_stride,
+                                                  n_lists, n_queries, k, out_ll, dists_out, ncand_out);
   return nlsh_check_cuda(nlsh_post_launch(), "merge_lists_kernel launch");
 }
 

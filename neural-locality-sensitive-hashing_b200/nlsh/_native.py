@@ -63,7 +63,7 @@ PROTOTYPES = {
     "nlsh_knn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "nlsh_knn_bruteforce": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _i64,
                                            _vp, _vp, _vp, _sz, _vp]),
-    "nlsh_merge_topk": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "nlsh_merge_topk": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "nlsh_recall_hits": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i64, _vp, _vp]),
     "nlsh_kernel_launch_count": (ctypes.c_longlong, []),
     "nlsh_profile_enable": (ctypes.c_int, [ctypes.c_int]),
@@ -273,8 +273,9 @@ def build_csr(codes, n_buckets, x=None):
 # query / kNN / merge
 # --------------------------------------------------------------------------------------
 def query_scan_topk(xq, probes, offsets, ids, x_sorted, d, max_bucket_rows, metric, k,
-                    id_offset=0, flags=0):
-    """-> (ids int64 [Q, k], dists fp32 [Q, k], n_cand int32 [Q])."""
+                    id_offset=0, flags=0, out=None):
+    """-> (ids int64 [Q, k], dists fp32 [Q, k], n_cand int32 [Q]); `out` = preallocated
+    contiguous (ids, dists, n_cand) tensors to write into."""
     xq = _f32c(xq, "query_vectors")
     require_cuda(probes, "probes")
     probes = probes.to(torch.int32).contiguous()
@@ -285,9 +286,15 @@ def query_scan_topk(xq, probes, offsets, ids, x_sorted, d, max_bucket_rows, metr
     n_buckets = offsets.shape[0] - 1
     n_rows = ids.shape[0]
     dev = xq.device
-    out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    out_n = torch.empty((nq,), dtype=torch.int32, device=dev)
+    if out is not None:
+        out_ids, out_d, out_n = out
+        assert out_ids.shape == (nq, k) and out_ids.dtype == torch.int64 and out_ids.is_contiguous()
+        assert out_d.shape == (nq, k) and out_d.dtype == torch.float32 and out_d.is_contiguous()
+        assert out_n.shape == (nq,) and out_n.dtype == torch.int32 and out_n.is_contiguous()
+    else:
+        out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_n = torch.empty((nq,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         nbytes = lib().nlsh_query_workspace_bytes(nq, p, k, d, n_buckets, n_rows, max_bucket_rows)
         ws = _workspace(dev, nbytes)
@@ -327,19 +334,35 @@ def knn_bruteforce(xq, xdb, metric, k, exclude_self=False, self_offset=0, id_off
     return out_ids, out_d
 
 
-def merge_topk(dists, ids):
-    """dists fp32 [G, Q, k] / ids int64 [G, Q, k] per-shard lists -> merged ([Q, k], [Q, k])."""
-    dists = _f32c(dists, "dists")
+def merge_topk(dists, ids, ncand=None):
+    """dists fp32 [G, Q, k] / ids int64 [G, Q, k] per-shard lists (the G dimension may be
+    strided, e.g. views into a packed all-gather buffer) -> merged ([Q, k] ids, [Q, k] dists
+    [, summed ncand int32 [Q] when per-shard ncand int32 [G, Q] is given])."""
+    require_cuda(dists, "dists")
     require_cuda(ids, "ids")
-    ids = ids.to(torch.int64).contiguous()
     g, nq, k = dists.shape
+    if dists.dtype != torch.float32 or ids.dtype != torch.int64:
+        dists, ids = dists.float(), ids.to(torch.int64)
+    if dists.stride()[1:] != (k, 1) or ids.stride()[1:] != (k, 1):
+        dists, ids = dists.contiguous(), ids.contiguous()
     dev = dists.device
     out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
     out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_n = None
+    n_stride = 0
+    if ncand is not None:
+        require_cuda(ncand, "ncand")
+        if ncand.dtype != torch.int32 or ncand.stride(1) != 1:
+            ncand = ncand.to(torch.int32).contiguous()
+        out_n = torch.empty((nq,), dtype=torch.int32, device=dev)
+        n_stride = ncand.stride(0) if g > 1 else nq
     with torch.cuda.device(dev):
-        rc = lib().nlsh_merge_topk(_ptr(dists), _ptr(ids), g, nq, k, _ptr(out_ids), _ptr(out_d),
-                                   _stream())
+        rc = lib().nlsh_merge_topk(_ptr(dists), _ptr(ids), dists.stride(0) if g > 1 else 0,
+                                   ids.stride(0) if g > 1 else 0, _ptr(ncand), n_stride, g, nq, k,
+                                   _ptr(out_ids), _ptr(out_d), _ptr(out_n), _stream())
     _check(rc, "nlsh_merge_topk")
+    if ncand is not None:
+        return out_ids, out_d, out_n
     return out_ids, out_d
 
 

@@ -202,7 +202,7 @@ class Indexer:
         return codes_to_sets(self.hash_tensors(query_vectors, hash_times))
 
     # ---- query ---------------------------------------------------------------------------
-    def query_tensors(self, query_vectors, k=10, hash_times=10, probes=None):
+    def query_tensors(self, query_vectors, k=10, hash_times=10, probes=None, out=None):
         """Batched search -> (ids int64 [Q, k], dists fp32 [Q, k], n_candidates int32 [Q]),
         all on the device, no host synchronisation.  ids are -1 / dists +inf past the number
         of candidates.  `probes` (int32 [Q, p], -1 = unused) overrides the hasher's probe
@@ -213,7 +213,7 @@ class Indexer:
         return _native.query_scan_topk(
             query_vectors, probes, self._offsets, self._ids, self._x_sorted, self._dim,
             self._max_bucket_rows, self._metric, k, id_offset=self._id_offset,
-            flags=self.scan_flags)
+            flags=self.scan_flags, out=out)
 
     def query(self, query_vectors, k=10, hash_times=10, probes=None) -> List[List[int]]:
         # indexer.py:56-96: returns (List[List[int]] ids by ascending distance, List[int]
@@ -231,11 +231,11 @@ class Indexer:
                 result[i] = [v for v in result[i] if v >= 0]
         return result, ncand_host.tolist()
 
-    def capture_query(self, n_queries, k=10, hash_times=10):
+    def capture_query(self, n_queries, k=10, hash_times=10, out=None):
         """CUDA-graph capture of query_tensors for a fixed batch shape: returns a GraphedQuery
         whose call replays hash -> probe selection -> scan + top-k (about a dozen launches) as
         one graph launch."""
-        return GraphedQuery(self, n_queries, k, hash_times)
+        return GraphedQuery(self, n_queries, k, hash_times, out=out)
 
     @staticmethod
     def probes_from_sets(sets, device, width=None):
@@ -256,7 +256,7 @@ class GraphedQuery:
     graph's static output tensors (ids int64 [Q, k], dists fp32 [Q, k], n_candidates int32 [Q]),
     overwritten by the next call."""
 
-    def __init__(self, indexer, n_queries, k=10, hash_times=10):
+    def __init__(self, indexer, n_queries, k=10, hash_times=10, out=None):
         dev = indexer._candidate_vectors_gpu.device
         self.indexer = indexer
         self.q = torch.zeros((n_queries, indexer._dim), dtype=torch.float32, device=dev)
@@ -264,12 +264,12 @@ class GraphedQuery:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):  # warm-up off the capture stream (sizes the workspace)
             for _ in range(2):
-                indexer.query_tensors(self.q, k, hash_times)
+                indexer.query_tensors(self.q, k, hash_times, out=out)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         launches0 = _native.kernel_launch_count()
         with torch.cuda.graph(self.graph):
-            self.ids, self.dists, self.ncand = indexer.query_tensors(self.q, k, hash_times)
+            self.ids, self.dists, self.ncand = indexer.query_tensors(self.q, k, hash_times, out=out)
         self.kernels_per_replay = _native.kernel_launch_count() - launches0
         # the captured kernels hold raw pointers into the scratch buffer: keep it alive
         self._keepalive = _native._workspaces.get((dev.type, dev.index))

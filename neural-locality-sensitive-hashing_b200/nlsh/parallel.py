@@ -35,6 +35,37 @@ def all_gather_topk(ids, dists, group=None):
     return g_ids.view(world, nq, k), g_d.view(world, nq, k)
 
 
+class PackedLists:
+    """One rank's search result as ONE byte buffer [ids int64 [Q,k] | dists fp32 [Q,k] | n_cand
+    int32 [Q]] so the exchange is a single all-gather; `gathered` holds all ranks' buffers and
+    exposes them as strided [G, Q, k] views the merge kernel reads in place."""
+
+    def __init__(self, n_queries, k, world, device):
+        self.nq, self.k, self.world = n_queries, k, world
+        self.off_d = n_queries * k * 8
+        self.off_n = self.off_d + n_queries * k * 4
+        self.nbytes = (self.off_n + n_queries * 4 + 15) // 16 * 16
+        self.local = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.gathered = torch.empty(world * self.nbytes, dtype=torch.uint8, device=device)
+        self.ids, self.dists, self.ncand = self._views(self.local.view(1, self.nbytes))
+        self.ids, self.dists, self.ncand = self.ids[0], self.dists[0], self.ncand[0]
+        self.g_ids, self.g_dists, self.g_ncand = self._views(self.gathered.view(world, self.nbytes))
+
+    def _views(self, buf):
+        g = buf.shape[0]
+        ids = buf[:, :self.off_d].view(torch.int64).view(g, self.nq, self.k)
+        dists = buf[:, self.off_d:self.off_n].view(torch.float32).view(g, self.nq, self.k)
+        ncand = buf[:, self.off_n:self.off_n + self.nq * 4].view(torch.int32).view(g, self.nq)
+        return ids, dists, ncand
+
+    def out(self):
+        return self.ids, self.dists, self.ncand
+
+    def exchange_and_merge(self, group=None):
+        dist.all_gather_into_tensor(self.gathered, self.local, group=group)
+        return _native.merge_topk(self.g_dists, self.g_ids, self.g_ncand)
+
+
 class ShardedIndexer:
     """Indexer over this rank's shard + cross-rank merge.  Same query API as Indexer."""
 
@@ -44,33 +75,35 @@ class ShardedIndexer:
         self.local = Indexer(hashing, local_vectors_gpu, distance_func, metric=metric,
                              id_offset=self.shard_lo)
 
+    def _multi(self):
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
     def query_tensors(self, query_vectors, k=10, hash_times=10, probes=None):
-        ids, dists, ncand = self.local.query_tensors(query_vectors, k, hash_times, probes)
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
-            return ids, dists, ncand
-        g_ids, g_d = all_gather_topk(ids, dists, self.group)
-        ncand = ncand.clone()
-        dist.all_reduce(ncand, group=self.group)
-        m_ids, m_d = _native.merge_topk(g_d, g_ids)
-        return m_ids, m_d, ncand
+        if not self._multi():
+            return self.local.query_tensors(query_vectors, k, hash_times, probes)
+        packed = PackedLists(query_vectors.shape[0], k, dist.get_world_size(self.group),
+                             query_vectors.device)
+        self.local.query_tensors(query_vectors, k, hash_times, probes, out=packed.out())
+        return packed.exchange_and_merge(self.group)
 
     def capture_query(self, n_queries, k=10, hash_times=10):
         """The local search (hash -> scan + top-k) as one CUDA graph; the all-gather and the
         merge of the shard lists stay eager launches behind it.  Returns a callable
         query_vectors -> (ids, dists, n_candidates); `.kernels_per_call` counts this library's
         kernels per call."""
-        graphed = self.local.capture_query(n_queries, k, hash_times)
-        multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        multi = self._multi()
+        packed = None
+        if multi:
+            dev = self.local._candidate_vectors_gpu.device
+            packed = PackedLists(n_queries, k, dist.get_world_size(self.group), dev)
+        graphed = self.local.capture_query(n_queries, k, hash_times,
+                                           out=packed.out() if multi else None)
 
         def run(query_vectors):
-            ids, dists, ncand = graphed(query_vectors)
+            res = graphed(query_vectors)
             if not multi:
-                return ids, dists, ncand
-            g_ids, g_d = all_gather_topk(ids, dists, self.group)
-            total = ncand.clone()
-            dist.all_reduce(total, group=self.group)
-            m_ids, m_d = _native.merge_topk(g_d, g_ids)
-            return m_ids, m_d, total
+                return res
+            return packed.exchange_and_merge(self.group)  # ONE all-gather + the merge kernel
 
         run.kernels_per_call = graphed.kernels_per_replay + (1 if multi else 0)
         run.graphed = graphed

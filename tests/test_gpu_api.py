@@ -159,3 +159,25 @@ def test_graphed_query_equals_eager():
     Qh = mixture(777, 64, 300, seed=77).pin_memory()
     g_ids, _, _ = graphed(Qh)
     assert torch.equal(g_ids, idx.query_tensors(Qh.cuda(), k=10, hash_times=4)[0])
+
+
+def test_packed_exchange_buffer_and_strided_merge(oracle):
+    # PackedLists: the [ids | dists | n_cand] byte buffer of one rank and the in-place strided
+    # views over the all-gathered buffers (the collective itself is covered by the gloo test
+    # and the multi-GPU bench)
+    from nlsh import _native
+    from nlsh.parallel import PackedLists
+    G, nq, k = 3, 41, 10
+    g = torch.Generator().manual_seed(3)
+    packs = [PackedLists(nq, k, G, torch.device("cuda")) for _ in range(G)]
+    all_d = torch.rand(G, nq, k, generator=g).sort(dim=2)[0]
+    all_i = torch.randint(0, 1 << 33, (G, nq, k), generator=g)
+    all_n = torch.randint(0, 1000, (G, nq), generator=g, dtype=torch.int32)
+    for r, pk in enumerate(packs):
+        pk.ids.copy_(all_i[r]); pk.dists.copy_(all_d[r]); pk.ncand.copy_(all_n[r])
+    gathered = torch.cat([pk.local for pk in packs])  # what all_gather_into_tensor produces
+    packs[0].gathered.copy_(gathered)
+    m_ids, m_d, m_n = _native.merge_topk(packs[0].g_dists, packs[0].g_ids, packs[0].g_ncand)
+    o_ids, o_d = oracle.merge_topk(all_d.numpy(), all_i.numpy(), k)
+    assert np.array_equal(m_ids.cpu().numpy(), o_ids) and np.array_equal(m_d.cpu().numpy(), o_d)
+    assert torch.equal(m_n.cpu(), all_n.sum(0).int())
