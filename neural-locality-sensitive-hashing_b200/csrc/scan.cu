@@ -1159,8 +1159,24 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
                                id_offset, ids_out, dists_out, ncand_out, st);
 }
 
-extern "C" size_t nlsh_knn_workspace_bytes(int64_t n_queries, int64_t n_rows, int32_t d, int32_t k) {
-  if (n_queries < 0 || n_rows < 0 || d < 1 || k < 1) return 0;
+// ---- tensor-core kNN (tc_knn.cu) -----------------------------------------------------------------
+bool nlsh_knn_tc_supported(int d, int metric, int k);
+int nlsh_knn_tc_blocks(long long n_queries, long long n_rows);
+size_t nlsh_knn_tc_scratch_floats(long long n_queries, long long n_rows, int d);
+int nlsh_knn_tc_run(const float* xq, long long n_queries, const float* xdb, long long n_rows, int d,
+                    int metric, int k, int exclude_self, long long self_offset, float* scratch,
+                    float* part_d, int* part_id, cudaStream_t st);
+
+namespace {
+// NLSH_KNN_IMPL=simt forces the fp32 SIMT scan kernel in dense mode (A/B runs); the default for the
+// precompute.py metrics (L2SQ / COSINE, the expansion-form distances) is the tensor-core GEMM.
+bool knn_use_tc(int d, int metric, int k, int64_t n_rows) {
+  const char* env = getenv("NLSH_KNN_IMPL");
+  if (env != nullptr && strcmp(env, "simt") == 0) return false;
+  return n_rows > 0 && nlsh_knn_tc_supported(d, metric, k);
+}
+
+size_t knn_simt_ws(int64_t n_queries, int64_t n_rows, int32_t d, int32_t k) {
   const KnnPlan kp = knn_plan(n_queries, n_rows);
   WorkspaceCarver ws(nullptr);
   ws.take<int>(64);
@@ -1170,6 +1186,27 @@ extern "C" size_t nlsh_knn_workspace_bytes(int64_t n_queries, int64_t n_rows, in
   ws.take<float>(lists);
   ws.take<int>(lists);
   return ws.total();
+}
+
+size_t knn_tc_ws(int64_t n_queries, int64_t n_rows, int32_t d, int32_t k) {
+  WorkspaceCarver ws(nullptr);
+  ws.take<float>(nlsh_knn_tc_scratch_floats(n_queries, n_rows, d));
+  const size_t lists = (size_t)n_queries * nlsh_knn_tc_blocks(n_queries, n_rows) * k;
+  ws.take<float>(lists);
+  ws.take<int>(lists);
+  return ws.total();
+}
+}  // namespace
+
+// The metric is not an argument: sized for whichever of the two implementations needs more.
+extern "C" size_t nlsh_knn_workspace_bytes(int64_t n_queries, int64_t n_rows, int32_t d, int32_t k) {
+  if (n_queries < 0 || n_rows < 0 || d < 1 || k < 1) return 0;
+  size_t need = knn_simt_ws(n_queries, n_rows, d, k);
+  if (knn_use_tc(d, NLSH_METRIC_L2SQ, k, n_rows)) {
+    const size_t tc = knn_tc_ws(n_queries, n_rows, d, k);
+    if (tc > need) need = tc;
+  }
+  return need;
 }
 
 extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const float* xdb,
@@ -1196,6 +1233,19 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
     return NLSH_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (knn_use_tc(d, metric, k, n_rows)) {
+    WorkspaceCarver tws(workspace);
+    float* scratch = tws.take<float>(nlsh_knn_tc_scratch_floats(n_queries, n_rows, d));
+    const int n_blocks = nlsh_knn_tc_blocks(n_queries, n_rows);
+    const size_t tlists = (size_t)n_queries * n_blocks * k;
+    float* t_d = tws.take<float>(tlists);
+    int* t_id = tws.take<int>(tlists);
+    const int rc = nlsh_knn_tc_run(xq, n_queries, xdb, n_rows, d, metric, k, exclude_self ? 1 : 0,
+                                   self_offset, scratch, t_d, t_id, st);
+    if (rc != NLSH_OK) return rc;
+    return launch_merge_partials(t_d, t_id, nullptr, nullptr, 1, 1, k, 0, n_blocks, 1, 0, n_queries,
+                                 id_offset, ids_out, dists_out, nullptr, st);
+  }
   const KnnPlan kp = knn_plan(n_queries, n_rows);
   WorkspaceCarver ws(workspace);
   int* counter = ws.take<int>(64);

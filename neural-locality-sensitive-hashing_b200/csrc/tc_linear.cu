@@ -19,15 +19,12 @@
 // accumulator completion to mbarriers; warps 0-3 are the epilogue: tcgen05.ld the 128 x N
 // accumulator (one row per thread), add bias, apply the activation, and either write the
 // next layer's hi/lo operands or the logits + bucket codes.
-#include <cuda.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
-constexpr int kTcBM = 128;      // rows per CTA = UMMA M
-constexpr int kTcBK = 32;       // fp32 per K block: 128 bytes = one SWIZZLE_128B row
 constexpr int kTcThreads = 192;
 
 struct TcArgs {
@@ -46,75 +43,6 @@ struct TcArgs {
   int n_main;         // TMEM accumulators for hi*hi (k-block kb uses kb % n_main); one more for the cross terms
   int tmem_cols;      // power of two >= max(32, (n_main + 1) * n_pad)
 };
-
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start address >> 4 in bits [0,14), LBO = 1 (unused for swizzled K-major) in [16,30),
-// SBO = 1024 bytes (one 8-row swizzle atom) >> 4 in [32,46), version 1 in [46,48),
-// layout type SWIZZLE_128B = 2 in [61,64).
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem_ptr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_u32(smem_ptr) >> 4) & 0x3FFFu);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, tf32 A and B, both
-// K-major, N >> 3 in bits [17,23), M >> 4 in bits [24,29).
-__device__ __forceinline__ uint32_t make_tf32_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
-}
-
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// All tcgen05 operations issued so far by this thread arrive on `bar` when they complete.
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
-
-// 16 consecutive accumulator columns of this thread's TMEM lane.
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ float tc_act(float v, int act, float scale) {
-  if (act == NLSH_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == NLSH_ACT_SIN) return sinf(scale * v);
-  return v;
-}
-
-__device__ __forceinline__ float tf32_hi(float x) {
-  return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
     tc_linear_kernel(const TcArgs a, const __grid_constant__ CUtensorMap map_a_hi,
@@ -147,11 +75,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     mbar_fence_init();
   }
   if (warp == 5) {  // one warp allocates the accumulator columns and owns the deallocation
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"((uint32_t)a.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tc_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   }
   tc_fence_before();
   __syncthreads();
@@ -272,9 +196,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)a.tmem_cols)
-                 : "memory");
+    tc_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
 }
 
@@ -290,6 +212,8 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, size_t n, float* 
     lo[j] = v - h;
   }
 }
+
+}  // namespace
 
 typedef CUresult (*TcEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -324,7 +248,6 @@ int tc_make_map(CUtensorMap* map, const float* base, long long rows, int cols, i
   return NLSH_OK;
 }
 
-}  // namespace
 
 // ---- interface used by hasher.cu ---------------------------------------------------------
 bool nlsh_tc_layer_supported(int in_dim, int out_dim) {

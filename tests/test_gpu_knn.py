@@ -75,10 +75,65 @@ def test_exclude_self_and_offsets():
     ids, _ = precompute.knn_tensors(X[200:300], X, "l2sq", 5, exclude_self=True, self_offset=200)
     assert not (ids == torch.arange(200, 300, device="cuda")[:, None]).any()
     ids0, d0 = precompute.knn_tensors(X[200:300], X, "l2sq", 5)
-    assert torch.equal(ids0[:, 0], torch.arange(200, 300, device="cuda")) and (d0[:, 0] == 0).all()
+    # expansion form (precompute._l2): d(x, x) is rounding noise on the scale of |x|^2, not exactly 0
+    assert torch.equal(ids0[:, 0], torch.arange(200, 300, device="cuda"))
+    assert (d0[:, 0].abs() <= 1e-5 * X[200:300].pow(2).sum(1)).all()
     assert torch.equal(ids0[:, 1:], ids[:, :4])
     ids_off, _ = precompute.knn_tensors(X[200:300], X, "l2sq", 5, id_offset=10_000_000_000)
     assert torch.equal(ids_off, ids0 + 10_000_000_000)
+
+
+@pytest.mark.parametrize("metric", ["l2sq", "cosine"])
+@pytest.mark.parametrize("nq,n,d,k", [(300, 70_000, 128, 10), (129, 5000, 100, 100), (1, 64, 4, 1),
+                                      (260, 100, 32, 128), (64, 1_200_000, 16, 10), (1000, 20_000, 64, 101)])
+def test_tensor_core_knn_matches_simt_and_oracle(oracle, metric, nq, n, d, k):
+    """tc_knn.cu (tcgen05 3xTF32 GEMM + top-k epilogue) against the fp32 SIMT path and the oracle."""
+    import os
+    import precompute
+    g = torch.Generator().manual_seed(7 * nq + n + d)
+    X = torch.randn(n, d, generator=g) + 0.5
+    Q = torch.randn(nq, d, generator=g) + 0.5
+    Xc, Qc = X.cuda(), Q.cuda()
+    os.environ["NLSH_KNN_IMPL"] = "simt"
+    try:
+        s_ids, s_d = precompute.knn_tensors(Qc, Xc, metric, k)
+    finally:
+        os.environ.pop("NLSH_KNN_IMPL")
+    t_ids, t_d = precompute.knn_tensors(Qc, Xc, metric, k)
+    kk = min(k, n)
+    assert (t_ids[:, kk:] == -1).all() and torch.isinf(t_d[:, kk:]).all()
+    t_ids, t_d, s_ids, s_d = (v.cpu().numpy()[:, :kk] for v in (t_ids, t_d, s_ids, s_d))
+    assert (np.diff(t_d, axis=1) >= 0).all()
+    for row in t_ids[:: max(1, nq // 50)]:
+        assert len(set(row.tolist())) == kk and row.min() >= 0 and row.max() < n
+    # distances: both are fp32 evaluations of the same quantity; the expansion form's rounding lives
+    # on the scale |q|^2 + |x|^2 (l2sq) or 1 (cosine)
+    if metric == "l2sq":
+        scale = (Q.pow(2).sum(1)[:, None] + X.pow(2).sum(1).max()).numpy()
+    else:
+        scale = np.ones((nq, 1), dtype=np.float32)
+    assert (np.abs(t_d - s_d) <= 2e-6 * scale).all(), np.abs(t_d - s_d).max()
+    mism = t_ids != s_ids
+    if mism.any():  # only where the two evaluations order a near-tie differently
+        qs, pos = np.nonzero(mism)
+        assert (np.abs(t_d[qs, pos] - s_d[qs, pos]) <= 2e-6 * scale[qs, 0]).all()
+        assert mism.mean() < 0.01, mism.mean()
+    if n <= 100_000 or nq <= 64:
+        o_ids, o_d = oracle.knn_queries(Q, X, metric, kk)
+        assert (np.abs(t_d - o_d) <= 1e-5 * scale).all()
+        assert (t_ids != o_ids).mean() < 0.01
+
+
+def test_tensor_core_knn_exclude_self_across_chunks():
+    import precompute
+    n = 1_100_000  # two database chunks of tc_knn.cu
+    X = torch.randn(n, 8, generator=torch.Generator().manual_seed(11)).cuda()
+    lo = 1_048_500  # queries whose own rows straddle the chunk boundary (2^20)
+    ids, _ = precompute.knn_tensors(X[lo:lo + 200], X, "l2sq", 3, exclude_self=True, self_offset=lo)
+    ids0, _ = precompute.knn_tensors(X[lo:lo + 200], X, "l2sq", 4)
+    own = torch.arange(lo, lo + 200, device="cuda")
+    assert not (ids == own[:, None]).any()
+    assert torch.equal(ids0[:, 0], own) and torch.equal(ids0[:, 1:], ids)
 
 
 def test_recall_kernel_matches_metrics():
