@@ -1161,7 +1161,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
 
 // ---- tensor-core kNN (tc_knn.cu) -----------------------------------------------------------------
 bool nlsh_knn_tc_supported(int d, int metric, int k);
-int nlsh_knn_tc_blocks(long long n_queries, long long n_rows);
+int nlsh_knn_tc_blocks(long long n_queries, long long n_rows, int k);
 size_t nlsh_knn_tc_scratch_floats(long long n_queries, long long n_rows, int d);
 int nlsh_knn_tc_run(const float* xq, long long n_queries, const float* xdb, long long n_rows, int d,
                     int metric, int k, int exclude_self, long long self_offset, float* scratch,
@@ -1191,7 +1191,7 @@ size_t knn_simt_ws(int64_t n_queries, int64_t n_rows, int32_t d, int32_t k) {
 size_t knn_tc_ws(int64_t n_queries, int64_t n_rows, int32_t d, int32_t k) {
   WorkspaceCarver ws(nullptr);
   ws.take<float>(nlsh_knn_tc_scratch_floats(n_queries, n_rows, d));
-  const size_t lists = (size_t)n_queries * nlsh_knn_tc_blocks(n_queries, n_rows) * k;
+  const size_t lists = (size_t)n_queries * nlsh_knn_tc_blocks(n_queries, n_rows, k) * k;
   ws.take<float>(lists);
   ws.take<int>(lists);
   return ws.total();
@@ -1236,7 +1236,7 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
   if (knn_use_tc(d, metric, k, n_rows)) {
     WorkspaceCarver tws(workspace);
     float* scratch = tws.take<float>(nlsh_knn_tc_scratch_floats(n_queries, n_rows, d));
-    const int n_blocks = nlsh_knn_tc_blocks(n_queries, n_rows);
+    const int n_blocks = nlsh_knn_tc_blocks(n_queries, n_rows, k);
     const size_t tlists = (size_t)n_queries * n_blocks * k;
     float* t_d = tws.take<float>(tlists);
     int* t_id = tws.take<int>(tlists);
