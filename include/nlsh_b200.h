@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NLSH_B200_VERSION 100 /* 0.1.0 */
+#define NLSH_B200_VERSION 200 /* 0.2.0: x_sqnorm in nlsh_build_csr / nlsh_query_scan_topk */
 
 #define NLSH_OK 0
 #define NLSH_ERR_INVALID (-1)   /* bad argument (-> ValueError in the Python layer) */
@@ -125,12 +125,14 @@ int nlsh_topp_probes(const float* logits, int64_t n, int32_t hash_size, int32_t 
  *   x_sorted_out fp32 [n, d_pad]       row i is x[ids_out[i]], d_pad = d rounded up to a multiple
  *                                      of 4 (zero filled) so every row starts 16-byte aligned for
  *                                      the bulk-async copies (may be NULL, then x may be NULL)
+ *   x_sqnorm_out fp32 [n]              |x_sorted row|^2 (may be NULL; needs x_sorted_out).  The
+ *                                      query path's tensor-core filter bounds distances with it.
  * codes must lie in [0, n_buckets).
  * ------------------------------------------------------------------------------------- */
 size_t nlsh_build_workspace_bytes(int64_t n, int32_t n_buckets);
 int nlsh_build_csr(const int32_t* codes, int64_t n, int32_t n_buckets, const float* x, int32_t d,
-                   int32_t* offsets_out, int32_t* ids_out, float* x_sorted_out, void* workspace,
-                   size_t workspace_bytes, void* stream);
+                   int32_t* offsets_out, int32_t* ids_out, float* x_sorted_out, float* x_sqnorm_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Query: multi-probe candidate scan + exact distance + top-k, batched over all queries.
@@ -140,19 +142,24 @@ int nlsh_build_csr(const int32_t* codes, int64_t n, int32_t n_buckets, const flo
  *   probes    device int32 [n_queries, p]; -1 = unused slot; duplicates inside a row are
  *             scanned once (the reference probes a Python set)
  *   offsets / ids / x_sorted: the CSR produced by nlsh_build_csr (x_sorted row stride d_pad)
+ *   x_sqnorm  device fp32 [n_rows] from nlsh_build_csr, or NULL.  With it (and d <= 128, k <= 32)
+ *             the scan runs a tcgen05 tf32 GEMM of each row tile against the bucket's queries as
+ *             a FILTER: pairs whose distance lower bound exceeds the query's current k-th best
+ *             are dropped, the rest are scored exactly as below.  Results are the same either way.
  *   max_bucket_rows: max over buckets of offsets[c+1]-offsets[c] (host knows it from build)
  *   ids_out   device int64 [n_queries, k]  row ids (+ id_offset) by ascending distance,
  *             ties broken by smaller id; -1 past the number of candidates
  *   dists_out device fp32 [n_queries, k]   +inf past the number of candidates
  *   ncand_out device int32 [n_queries]     candidates scanned (indexer.py:71,94)
- *   flags: bit 0 = use the synchronous-staging kernel instead of the bulk-async (TMA) ring
- *          (debug / A-B only)
+ *   flags: bit 0 = use the synchronous-staging kernel instead of the bulk-async (TMA) ring;
+ *          bit 1 = do not use the tensor-core filter even when x_sqnorm is given (debug / A-B only)
  * ------------------------------------------------------------------------------------- */
 size_t nlsh_query_workspace_bytes(int64_t n_queries, int32_t p, int32_t k, int32_t d,
                                   int32_t n_buckets, int64_t n_rows, int64_t max_bucket_rows);
 int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t d, const int32_t* probes,
                          int32_t p, const int32_t* offsets, int32_t n_buckets, const int32_t* ids,
-                         const float* x_sorted, int64_t n_rows, int64_t max_bucket_rows,
+                         const float* x_sorted, const float* x_sqnorm, int64_t n_rows,
+                         int64_t max_bucket_rows,
                          int32_t metric, int32_t k, int64_t id_offset, int64_t* ids_out,
                          float* dists_out, int32_t* ncand_out, void* workspace,
                          size_t workspace_bytes, uint32_t flags, void* stream);

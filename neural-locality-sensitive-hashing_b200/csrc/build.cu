@@ -193,7 +193,7 @@ __global__ void extract_offsets_kernel(const int* __restrict__ cursor, long long
 template <bool VEC>
 __global__ void __launch_bounds__(256)
     gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ ids, long long n, int d,
-                       float* __restrict__ x_sorted) {
+                       float* __restrict__ x_sorted, float* __restrict__ x_sqnorm) {
   constexpr int R = 4;
   const int lane = lane_id();
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -202,6 +202,9 @@ __global__ void __launch_bounds__(256)
     long long src[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) src[r] = (i0 + r < n) ? (long long)ids[i0 + r] : -1;
+    float ss[R];  // |row|^2 (the tensor-core scan's filter needs it; scan_tc.cu)
+#pragma unroll
+    for (int r = 0; r < R; ++r) ss[r] = 0.f;
     if (VEC) {
       const int nv = d >> 2;
       for (int v0 = 0; v0 < nv; v0 += 32) {
@@ -213,8 +216,13 @@ __global__ void __launch_bounds__(256)
             val[r] = __ldcs(reinterpret_cast<const float4*>(x + (size_t)src[r] * d) + v);
 #pragma unroll
         for (int r = 0; r < R; ++r)
-          if (src[r] >= 0 && v < nv)
+          if (src[r] >= 0 && v < nv) {
             __stcs(reinterpret_cast<float4*>(x_sorted + (size_t)(i0 + r) * d) + v, val[r]);
+            ss[r] = fmaf(val[r].x, val[r].x, ss[r]);
+            ss[r] = fmaf(val[r].y, val[r].y, ss[r]);
+            ss[r] = fmaf(val[r].z, val[r].z, ss[r]);
+            ss[r] = fmaf(val[r].w, val[r].w, ss[r]);
+          }
       }
     } else {
       const int d_pad = (d + 3) / 4 * 4;  // rows of x_sorted are zero-padded to 16 bytes
@@ -222,8 +230,20 @@ __global__ void __launch_bounds__(256)
         const int c = c0 + lane;
 #pragma unroll
         for (int r = 0; r < R; ++r)
-          if (src[r] >= 0 && c < d_pad)
-            x_sorted[(size_t)(i0 + r) * d_pad + c] = c < d ? x[(size_t)src[r] * d + c] : 0.f;
+          if (src[r] >= 0 && c < d_pad) {
+            const float v = c < d ? x[(size_t)src[r] * d + c] : 0.f;
+            x_sorted[(size_t)(i0 + r) * d_pad + c] = v;
+            ss[r] = fmaf(v, v, ss[r]);
+          }
+      }
+    }
+    if (x_sqnorm != nullptr) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float t = ss[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(NLSH_FULL_MASK, t, o);
+        if (lane == 0 && src[r] >= 0) x_sqnorm[i0 + r] = t;
       }
     }
   }
@@ -242,8 +262,8 @@ extern "C" size_t nlsh_build_workspace_bytes(int64_t n, int32_t n_buckets) {
 
 extern "C" int nlsh_build_csr(const int32_t* codes, int64_t n, int32_t n_buckets, const float* x,
                               int32_t d, int32_t* offsets_out, int32_t* ids_out,
-                              float* x_sorted_out, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+                              float* x_sorted_out, float* x_sqnorm_out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   NLSH_REQUIRE(n >= 0 && n < (1ll << 31), "build: n=%lld outside [0, 2^31)", (long long)n);
   NLSH_REQUIRE(n_buckets >= 1 && n_buckets <= (1 << 20), "build: n_buckets=%d outside [1, 2^20]",
                n_buckets);
@@ -251,6 +271,7 @@ extern "C" int nlsh_build_csr(const int32_t* codes, int64_t n, int32_t n_buckets
   NLSH_REQUIRE(n == 0 || (codes != nullptr && ids_out != nullptr), "build: null codes / ids_out");
   NLSH_REQUIRE(x_sorted_out == nullptr || n == 0 || (x != nullptr && d >= 1),
                "build: x_sorted_out given without x / d");
+  NLSH_REQUIRE(x_sqnorm_out == nullptr || x_sorted_out != nullptr, "build: x_sqnorm_out needs x_sorted_out");
   const size_t need = nlsh_build_workspace_bytes(n, n_buckets);
   if (workspace == nullptr || workspace_bytes < need) {
     nlsh_set_error("build: workspace %zu bytes < required %zu", workspace_bytes, need);
@@ -291,9 +312,9 @@ extern "C" int nlsh_build_csr(const int32_t* codes, int64_t n, int32_t n_buckets
       const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(x_sorted_out) & 15) == 0);
       if (vec)
-        gather_rows_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(x, ids_out, n, d, x_sorted_out);
+        gather_rows_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(x, ids_out, n, d, x_sorted_out, x_sqnorm_out);
       else
-        gather_rows_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(x, ids_out, n, d, x_sorted_out);
+        gather_rows_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(x, ids_out, n, d, x_sorted_out, x_sqnorm_out);
       NLSH_CUDA_TRY(nlsh_post_launch());
     }
   }

@@ -27,6 +27,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "scan_tc.cuh"
 
 namespace {
 
@@ -113,12 +114,12 @@ struct ScanPolicy {
 };
 
 ScanPolicy scan_policy(int64_t n_queries, int p, int n_buckets, int64_t n_rows,
-                       int64_t max_bucket_rows) {
-  const int64_t grid = (int64_t)nlsh_num_sms() * 2;
+                       int64_t max_bucket_rows, int group = kG, int ctas_per_sm = 2) {
+  const int64_t grid = (int64_t)nlsh_num_sms() * ctas_per_sm;
   const int64_t target_items = grid * 8;
   const int64_t pairs = n_queries * p > 0 ? n_queries * p : 1;
   const int64_t distinct = pairs < n_buckets ? pairs : n_buckets;
-  int64_t groups = pairs / kG;
+  int64_t groups = pairs / group;
   if (groups < distinct) groups = distinct;
   if (groups < 1) groups = 1;
   const int64_t chunks_needed = (target_items + groups - 1) / groups;
@@ -340,6 +341,44 @@ __global__ void plan_items_kernel(const ScanArgs a, ItemRec* __restrict__ out, i
     for (int g = 0; g < kG; ++g)
       r.f[g] = g < it.ng ? (a.dense ? it.pair_base + g : a.pairs[it.pair_base + g]) : -1;
     r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = 0;
+    out[i] = r;
+  }
+}
+
+// Items of the tensor-core scan (scan_tc.cu): (bucket, row chunk, group of <= kTcNQ pairs).
+__global__ void plan_tc_items_kernel(const int* __restrict__ item_off, const int* __restrict__ pair_off,
+                                     const int* __restrict__ offsets, int n_buckets, int rchunk,
+                                     int max_chunks, TcItem* __restrict__ out, int max_items) {
+  int total = item_off[n_buckets];
+  if (total > max_items) total = max_items;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_buckets;  // largest b with item_off[b] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (item_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int b = lo;
+    const int local = i - item_off[b];
+    const int p0 = pair_off[b];
+    const int nq = pair_off[b + 1] - p0;
+    const int ngroups = (nq + kTcNQ - 1) / kTcNQ;
+    const int c = local / ngroups;
+    const int gq = local - c * ngroups;
+    const int r0 = offsets[b];
+    const int size = offsets[b + 1] - r0;
+    const int nch = chunk_count(size, rchunk, max_chunks);
+    const int rc = chunk_rows(size, nch);
+    long long c_lo = (long long)c * rc, c_hi = c_lo + rc;
+    if (c_lo > size) c_lo = size;
+    if (c_hi > size || c == nch - 1) c_hi = size;
+    TcItem r;
+    r.row0 = r0 + (int)c_lo;
+    r.row1 = r0 + (int)c_hi;
+    r.pair_base = p0 + gq * kTcNQ;
+    const int left = nq - gq * kTcNQ;
+    r.nq = left < kTcNQ ? left : kTcNQ;
+    r.chunk = c;
+    r.pad[0] = r.pad[1] = r.pad[2] = 0;
     out[i] = r;
   }
 }
@@ -671,7 +710,7 @@ __global__ void plan_count_kernel(const int* __restrict__ probes, const int* __r
 // One block: pair_off = exclusive scan of cnt, item_off = exclusive scan of items per bucket.
 __global__ void __launch_bounds__(1024)
     plan_scan_kernel(const int* __restrict__ cnt, const int* __restrict__ offsets, int n_buckets,
-                     int rchunk, int max_chunks, int* __restrict__ pair_off,
+                     int rchunk, int max_chunks, int group, int* __restrict__ pair_off,
                      int* __restrict__ item_off) {
   __shared__ int sw[2][33];
   int carry_p = 0, carry_i = 0;
@@ -682,7 +721,7 @@ __global__ void __launch_bounds__(1024)
     if (b < n_buckets) {
       c = cnt[b];
       const int size = offsets[b + 1] - offsets[b];
-      items = ((c + kG - 1) / kG) * chunk_count(size, rchunk, max_chunks);
+      items = ((c + group - 1) / group) * chunk_count(size, rchunk, max_chunks);
     }
     int ic = c, ii = items;
 #pragma unroll
@@ -1003,12 +1042,20 @@ struct QueryWorkspace {
   int max_items;
   float* part_d;
   int* part_id;
+  // tensor-core scan extras
+  float* qs;        // [Q*p (+ kTcNQ), d_pad] queries in pair order
+  float* qs_norm;   // [Q*p]
+  float* tau_g;     // [Q]
+  TcItem* tc_items; // [max_tc_items]
+  int max_tc_items;
   size_t zero_ints;
   size_t total;
 };
 
+// max_chunks / tc_max_chunks: chunks of the largest bucket under the SIMT / tensor-core policy
+// (tc_max_chunks = 0: no tensor-core extras).
 QueryWorkspace carve_query_ws(void* base, int64_t nq, int p, int k, int d, int n_buckets,
-                              int max_chunks) {
+                              int max_chunks, int tc_max_chunks) {
   QueryWorkspace w;
   WorkspaceCarver ws(base);
   w.zero_ints = (size_t)2 * n_buckets + 64;
@@ -1026,9 +1073,23 @@ QueryWorkspace carve_query_ws(void* base, int64_t nq, int p, int k, int d, int n
   if (mi > (1ll << 30)) mi = 1ll << 30;
   w.max_items = (int)mi;
   w.items = ws.take<ItemRec>((size_t)w.max_items);
-  const size_t lists = (size_t)nq * p * max_chunks * k;
+  const int list_chunks = max_chunks > tc_max_chunks ? max_chunks : tc_max_chunks;
+  const size_t lists = (size_t)nq * p * list_chunks * k;
   w.part_d = ws.take<float>(lists);
   w.part_id = ws.take<int>(lists);
+  w.qs = w.qs_norm = w.tau_g = nullptr;
+  w.tc_items = nullptr;
+  w.max_tc_items = 0;
+  if (tc_max_chunks > 0) {
+    const size_t d_pad = (size_t)((d + 3) / 4 * 4);
+    w.qs = ws.take<float>((size_t)(pairs + kTcNQ) * d_pad);
+    w.qs_norm = ws.take<float>((size_t)pairs + kTcNQ);
+    w.tau_g = ws.take<float>((size_t)nq);
+    int64_t mt = (pairs / kTcNQ + (pairs < n_buckets ? pairs : n_buckets) + 1) * tc_max_chunks;
+    if (mt > (1ll << 30)) mt = 1ll << 30;
+    w.max_tc_items = (int)mt;
+    w.tc_items = ws.take<TcItem>((size_t)w.max_tc_items);
+  }
   w.total = ws.total();
   return w;
 }
@@ -1060,18 +1121,31 @@ KnnPlan knn_plan(int64_t n_queries, int64_t n_rows) {
 
 }  // namespace
 
+namespace {
+// NLSH_SCAN_IMPL=simt forces the fp32 SIMT scan kernel (A/B runs).
+bool scan_use_tc(int d, int k, int metric) {
+  const char* env = getenv("NLSH_SCAN_IMPL");
+  if (env != nullptr && strcmp(env, "simt") == 0) return false;
+  return nlsh_scan_tc_supported(d, k, metric);
+}
+}  // namespace
+
 extern "C" size_t nlsh_query_workspace_bytes(int64_t n_queries, int32_t p, int32_t k, int32_t d,
                                              int32_t n_buckets, int64_t n_rows,
                                              int64_t max_bucket_rows) {
   if (n_queries < 0 || p < 1 || k < 1 || d < 1 || n_buckets < 1) return 0;
   const ScanPolicy pol = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows);
-  return carve_query_ws(nullptr, n_queries, p, k, d, n_buckets, pol.max_chunks).total;
+  int tc_chunks = 0;  // the metric is not an argument: sized for either scan implementation
+  if (scan_use_tc(d, k, NLSH_METRIC_L2))
+    tc_chunks = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows, kTcNQ, 1).max_chunks;
+  return carve_query_ws(nullptr, n_queries, p, k, d, n_buckets, pol.max_chunks, tc_chunks).total;
 }
 
 extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t d,
                                     const int32_t* probes, int32_t p, const int32_t* offsets,
                                     int32_t n_buckets, const int32_t* ids, const float* x_sorted,
-                                    int64_t n_rows, int64_t max_bucket_rows, int32_t metric,
+                                    const float* x_sqnorm, int64_t n_rows, int64_t max_bucket_rows,
+                                    int32_t metric,
                                     int32_t k, int64_t id_offset, int64_t* ids_out,
                                     float* dists_out, int32_t* ncand_out, void* workspace,
                                     size_t workspace_bytes, uint32_t flags, void* stream) {
@@ -1091,14 +1165,22 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   NLSH_REQUIRE(n_rows == 0 || (ids && x_sorted), "query: null index arrays");
   NLSH_REQUIRE((reinterpret_cast<uintptr_t>(x_sorted) & 15) == 0, "query: x_sorted not 16-byte aligned");
 
-  const ScanPolicy pol = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows);
-  const QueryWorkspace w = carve_query_ws(workspace, n_queries, p, k, d, n_buckets, pol.max_chunks);
+  const ScanPolicy pol_simt = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows);
+  const bool tc_sized = scan_use_tc(d, k, NLSH_METRIC_L2);
+  ScanPolicy pol_tc = pol_simt;
+  if (tc_sized) pol_tc = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows, kTcNQ, 1);
+  const QueryWorkspace w = carve_query_ws(workspace, n_queries, p, k, d, n_buckets, pol_simt.max_chunks,
+                                          tc_sized ? pol_tc.max_chunks : 0);
   if (workspace == nullptr || workspace_bytes < w.total) {
     nlsh_set_error("query: workspace %zu bytes < required %zu", workspace_bytes, w.total);
     return NLSH_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool async = (flags & 1u) == 0;
+  // tensor-core filtered scan (scan_tc.cu) whenever the index carries the row norms
+  const bool use_tc = tc_sized && async && (flags & 2u) == 0 && x_sqnorm != nullptr && n_rows > 0 &&
+                      scan_use_tc(d, k, metric);
+  const ScanPolicy pol = use_tc ? pol_tc : pol_simt;
   const ScanGeom geom = scan_geom(d, k, async);
   const long long n_pairs = (long long)n_queries * p;
 
@@ -1107,7 +1189,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
                                                                      n_pairs, w.cnt);
   NLSH_CUDA_TRY(nlsh_post_launch());
   plan_scan_kernel<<<1, 1024, 0, st>>>(w.cnt, offsets, n_buckets, pol.rchunk, pol.max_chunks,
-                                       w.pair_off, w.item_off);
+                                       use_tc ? kTcNQ : kG, w.pair_off, w.item_off);
   NLSH_CUDA_TRY(nlsh_post_launch());
   plan_scatter_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(
       probes, offsets, n_buckets, p, n_pairs, w.pair_off, w.cursor, w.pairs);
@@ -1117,6 +1199,44 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
       xq, n_queries, d, geom.d_pad, metric == NLSH_METRIC_ANGULAR ? 1 : 0, w.qn);
   NLSH_CUDA_TRY(nlsh_post_launch());
   const float* q_used = w.qn;
+
+  if (use_tc) {
+    plan_tc_items_kernel<<<nlsh_num_sms() * 4, 256, 0, st>>>(w.item_off, w.pair_off, offsets, n_buckets,
+                                                             pol.rchunk, pol.max_chunks, w.tc_items,
+                                                             w.max_tc_items);
+    NLSH_CUDA_TRY(nlsh_post_launch());
+    int rc = nlsh_scan_tc_prepare(w.qn, w.pairs, w.pair_off + n_buckets, n_pairs, p, geom.d_pad, w.qs,
+                                  w.qs_norm, w.tau_g, n_queries, st);
+    if (rc != NLSH_OK) return rc;
+    TcScanArgs t{};
+    t.xs = x_sorted;
+    t.xnorm = x_sqnorm;
+    t.ids = ids;
+    t.qs = w.qs;
+    t.qs_norm = w.qs_norm;
+    t.pairs = w.pairs;
+    t.items = w.tc_items;
+    t.n_items = w.item_off + n_buckets;
+    t.max_items = w.max_tc_items;
+    t.item_counter = w.counter;
+    t.tau_g = w.tau_g;
+    t.part_d = w.part_d;
+    t.part_id = w.part_id;
+    t.n_rows = n_rows;
+    t.n_pairs = n_pairs;
+    t.p = p;
+    t.k = k;
+    t.d = geom.d;
+    t.d_pad = geom.d_pad;
+    t.max_chunks = pol.max_chunks;
+    nlsh_profile_mark(st, true);
+    rc = nlsh_scan_tc_launch(metric, t, st);
+    nlsh_profile_mark(st, false);
+    if (rc != NLSH_OK) return rc;
+    return launch_merge_partials(w.part_d, w.part_id, probes, offsets, n_buckets, p, k, pol.rchunk,
+                                 pol.max_chunks, 0, metric == NLSH_METRIC_L2 ? 1 : 0, n_queries,
+                                 id_offset, ids_out, dists_out, ncand_out, st);
+  }
 
   ScanArgs a{};
   a.xs = x_sorted;

@@ -1,0 +1,486 @@
+// Candidate scan with a tensor-core FILTER in front of the exact distance (the default path of
+// nlsh_query_scan_topk for d <= 128, k <= 32).  Same job as scan.cu::scan_kernel - the per-query
+// gather + distance_func + topk of Indexer.query (nlsh/indexer.py:62-95) - and the same results:
+// every distance that enters a top-k list is computed in fp32 in the reference's difference form
+// (nlsh/data.py:201 F.pairwise_distance, nlsh/data.py:109 1 - cosine_similarity), never from the
+// GEMM expansion.  The GEMM only decides which (row, query) pairs cannot matter.
+//
+// Why: with the 10k-query batches of the BASELINE configs every bucket is probed by ~20 queries.
+// The fp32 SIMT kernel fetches a bucket tile once for all of them but still pays 3 lane-ops per
+// (row, query, column): ncu showed it fp32-issue bound (fma pipe 59 %, DRAM 43 %).  Here one
+// tcgen05.mma (kind::tf32, raw fp32 bits as operands) produces the 128 x 32 dot products of a row
+// tile against the item's queries into TMEM; an epilogue thread per row turns each into a LOWER
+// BOUND of the exact distance and compares it with the query's current threshold.  Survivors
+// (a few per tile once the lists are warm) are re-scored exactly from the tile that is still in
+// shared memory, and inserted into register-resident sorted lists.  The kernel is then bound by
+// streaming x_sorted from HBM, which is the roofline SURVEY 8(d) names for the scan.
+//
+// Exactness of the filter.  tf32 keeps 10 mantissa bits of each operand, so
+// |dot_tc - <q, x>| <= 2^-9 * 1.02 * |q| |x|  (Cauchy-Schwarz; the 1.02 covers the fp32 accumulate).
+//   L2:  d2 = |q|^2 + |x|^2 - 2 <q,x> >= (1 - c)(|q|^2 + |x|^2) - 2 dot_tc,  c = 2^-9 * 1.02 + 4e-5
+//        (the 4e-5 covers fp32 rounding of the two norms).  The list holds the reference's
+//        D = sum((q - x + 1e-6)^2) >= d2 - 2e-6 sqrt(dim) sqrt(d2) - 1e-5 D, so a pair whose bound
+//        exceeds tau_eff = y + a sqrt(y) + a^2  (y = tau * 1.0001, a = 2.1e-6 sqrt(dim)) has D > tau.
+//   angular: 1 - cos >= 1 - dot_tc / |x| - 2.1e-3.
+// A pair is dropped only when its bound is above the threshold, so the top-k is the same set the
+// SIMT kernel finds; ties are still broken by the (distance, id) order.
+//
+// The threshold of a query is min(k-th best of this item's list, tau_g[query]) where tau_g is a
+// global per-query upper bound of the final k-th distance, lowered (atomicMin) whenever an item
+// finishes with a full list: the 8 probes of a query tighten each other.  Any k-th-best of any
+// subset of the candidates is such an upper bound, so the merged result does not depend on the
+// order items happen to run in.
+//
+// Roles in a CTA (one persistent CTA per SM, 192 threads):
+//   warp 0 lane 0  producer: owns the work queue (atomic counter), per item TMA-loads the item's
+//                  queries (box 32 rows x 32 fp32 per K block, SWIZZLE_128B) into a 2-deep ring and
+//                  streams row tiles (box 128 rows x 32 fp32) into the slot ring;
+//   warp 1 lane 0  MMA issuer: per tile, per K block 4 x tcgen05.mma M128 N32 K8 into one of two
+//                  TMEM accumulator sets; tcgen05.commit -> acc_full;
+//   warps 2-5      epilogue: (1) filter: thread = row, tcgen05.ld its 32 scores, bound + compare,
+//                  survivors binned per query in shared memory (warp-aggregated atomics);
+//                  (2) re-rank: each warp owns 8 of the item's queries; 4 lanes per survivor compute
+//                  the exact distance from the swizzled tile, WarpTopK::offer inserts.
+#include <string.h>
+
+#include "scan_tc.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kEpiWarps = 4;
+constexpr int kTile = 128;                      // rows per tile = UMMA M
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // 192
+constexpr int kOwn = kTcNQ / kEpiWarps;         // lists per epilogue warp
+constexpr uint32_t kSlotBytes = kTile * kTcBK * sizeof(float);   // 16 KB: one K block of a row tile
+constexpr uint32_t kQBoxBytes = kTcNQ * kTcBK * sizeof(float);   // 4 KB: one K block of the queries
+constexpr int kMaxSlots = 16;
+constexpr int kMaxKBlocks = 4;                  // d_pad <= 128
+constexpr float kFilterC = 0.001953125f * 1.02f + 4e-5f;  // see header comment
+constexpr float kAngularC = 2.1e-3f;
+
+__device__ __forceinline__ float pos_inf() { return __int_as_float(0x7f800000); }
+__device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+
+// Filter threshold of a query from the best known bound `eff` of its k-th distance.
+template <int METRIC>
+__device__ __forceinline__ float make_thr(float eff, float qn2, float l2_slack) {
+  if (eff == pos_inf()) return pos_inf();
+  if (METRIC == NLSH_METRIC_L2) {
+    if (!(eff >= 0.f)) return neg_inf();
+    const float y = eff * 1.0001f;
+    const float te = (y + l2_slack * sqrtf(y) + l2_slack * l2_slack) * 1.0001f + 1e-30f;
+    return te - (1.0f - kFilterC) * qn2;
+  }
+  return eff - 1.0f + kAngularC;
+}
+
+// Exact distance of row r of the tile to query j of the item, 4 lanes per pair: lane l4 owns the
+// columns = l4 (mod 4) and walks them in ascending order, the columns of a partial last float4
+// (d % 4 != 0) go to lane 0, and the four partial sums are combined as (s0 + s1) + (s2 + s3).
+// That is exactly the summation order of scan.cu::consume_box (packed float2 accumulators over the
+// columns 0,1 / 2,3 of each float4), so both scan kernels produce the same bits for the same
+// (q, x) - the parity tests compare them with torch.equal.  Both operands sit in SWIZZLE_128B
+// boxes: 16-byte chunk c of row r is stored at chunk position c ^ (r & 7).  L2 returns the
+// squared distance (the root is taken in merge_partials_kernel).
+template <int METRIC>
+__device__ __noinline__ float exact_distance(const unsigned char* slots, unsigned ring, unsigned n_slots,
+                                             const unsigned char* qsrc, int d, int r, int j, int l4) {
+  float acc = 0.f, xx = 0.f;
+  const int nv = d >> 2, tail = d & 3;
+  const int xrow = r * 128 + l4 * 4, xsw = r & 7;
+  const int qrow = j * 128 + l4 * 4, qsw = j & 7;
+#pragma unroll
+  for (int kb = 0; kb < kMaxKBlocks; ++kb) {
+    if (kb * 8 < nv) {
+      const unsigned char* xs = slots + (size_t)((ring + (unsigned)kb) % n_slots) * kSlotBytes + xrow;
+      const unsigned char* qs = qsrc + kb * kQBoxBytes + qrow;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        if (kb * 8 + c8 < nv) {
+          const float x = *reinterpret_cast<const float*>(xs + ((c8 ^ xsw) << 4));
+          const float q = *reinterpret_cast<const float*>(qs + ((c8 ^ qsw) << 4));
+          if (METRIC == NLSH_METRIC_L2) {
+            // F.pairwise_distance: (q - x) + eps, squared and summed (nlsh/data.py:201)
+            const float t = __fadd_rn(__fsub_rn(q, x), 1e-6f);
+            acc = fmaf(t, t, acc);
+          } else {
+            acc = fmaf(q, x, acc);
+            xx = fmaf(x, x, xx);
+          }
+        }
+      }
+    }
+  }
+  if (tail != 0 && l4 == 0) {  // the partial float4 at vector index nv: columns 4 nv .. d - 1
+    const int kb = nv >> 3, c8 = nv & 7;
+    const float* xs = reinterpret_cast<const float*>(
+        slots + (size_t)((ring + (unsigned)kb) % n_slots) * kSlotBytes + r * 128 + ((c8 ^ xsw) << 4));
+    const float* qs = reinterpret_cast<const float*>(qsrc + kb * kQBoxBytes + j * 128 + ((c8 ^ qsw) << 4));
+    for (int c = 0; c < tail; ++c) {
+      if (METRIC == NLSH_METRIC_L2) {
+        const float t = __fadd_rn(__fsub_rn(qs[c], xs[c]), 1e-6f);
+        acc = fmaf(t, t, acc);
+      } else {
+        acc = fmaf(qs[c], xs[c], acc);
+        xx = fmaf(xs[c], xs[c], xx);
+      }
+    }
+  }
+  acc += __shfl_xor_sync(NLSH_FULL_MASK, acc, 1);
+  acc += __shfl_xor_sync(NLSH_FULL_MASK, acc, 2);
+  if (METRIC == NLSH_METRIC_L2) return acc;
+  xx += __shfl_xor_sync(NLSH_FULL_MASK, xx, 1);
+  xx += __shfl_xor_sync(NLSH_FULL_MASK, xx, 2);
+  return 1.0f - acc / fmaxf(sqrtf(xx), 1e-8f);  // nlsh/data.py:109, norms clamped at 1e-8
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(kThreads, 1)
+    scan_tc_kernel(const TcScanArgs a, const __grid_constant__ CUtensorMap map_x,
+                   const __grid_constant__ CUtensorMap map_q) {
+  extern __shared__ unsigned char stc_smem_raw[];
+  unsigned char* base = stc_smem_raw + ((1024u - (smem_u32(stc_smem_raw) & 1023u)) & 1023u);
+  unsigned char* slots = base;                                              // [n_slots][16 KB]
+  unsigned char* qbuf = slots + (size_t)a.n_slots * kSlotBytes;             // [2][kblocks][4 KB]
+  unsigned char* qrows = qbuf + (size_t)2 * a.kblocks * kQBoxBytes;         // [kTcNQ][kTile] survivor rows
+  int* id_s = reinterpret_cast<int*>(qrows + kTcNQ * kTile);                // [kTile]
+  float* thr = reinterpret_cast<float*>(id_s + kTile);                      // [kTcNQ]
+  int* cnt = reinterpret_cast<int*>(thr + kTcNQ);                           // [2][kTcNQ]
+  TcItem* itm = reinterpret_cast<TcItem*>(cnt + 2 * kTcNQ);                 // [2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(itm + 2);                // [kMaxSlots]
+  uint64_t* empty_bar = full_bar + kMaxSlots;                               // [kMaxSlots]
+  uint64_t* q_full = empty_bar + kMaxSlots;                                 // [2]
+  uint64_t* q_empty = q_full + 2;                                           // [2]
+  uint64_t* acc_full = q_empty + 2;                                         // [2]
+  uint64_t* acc_empty = acc_full + 2;                                       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const unsigned n_slots = (unsigned)a.n_slots;
+  const int kblocks = a.kblocks;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.n_slots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kEpiWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], kEpiWarps);
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (tid < 2 * kTcNQ) cnt[tid] = 0;
+  if (warp == 1) tc_alloc(tmem_slot, 64);  // two accumulator sets of kTcNQ columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =================================== producer =========================================
+    if (lane == 0) {
+      int total = *a.n_items;
+      if (total > a.max_items) total = a.max_items;
+      unsigned ring = 0, icount = 0;
+      while (true) {
+        const int item = atomicAdd(a.item_counter, 1);
+        const int islot = (int)(icount & 1u);
+        mbar_wait(&q_empty[islot], ((icount >> 1) & 1u) ^ 1u);
+        if (item >= total) {
+          itm[islot].nq = 0;  // end of work
+          mbar_arrive(&q_full[islot]);
+          break;
+        }
+        const TcItem rec = a.items[item];
+        itm[islot] = rec;
+        mbar_arrive_expect_tx(&q_full[islot], (unsigned)kblocks * kQBoxBytes);
+        unsigned char* qdst = qbuf + (size_t)islot * kblocks * kQBoxBytes;
+        for (int kb = 0; kb < kblocks; ++kb)
+          tma_load_2d(qdst + kb * kQBoxBytes, &map_q, kb * kTcBK, rec.pair_base, &q_full[islot]);
+        const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
+        for (int t = 0; t < n_tiles; ++t) {
+          const int trow0 = rec.row0 + t * kTile;
+          for (int kb = 0; kb < kblocks; ++kb, ++ring) {
+            const unsigned s = ring % n_slots;
+            mbar_wait(&empty_bar[s], ((ring / n_slots) & 1u) ^ 1u);
+            // a box is always written in full (rows / columns past the tensor are zero filled)
+            mbar_arrive_expect_tx(&full_bar[s], kSlotBytes);
+            tma_load_2d(slots + (size_t)s * kSlotBytes, &map_x, kb * kTcBK, trow0, &full_bar[s]);
+          }
+        }
+        ++icount;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = make_tf32_idesc(kTcNQ);
+      unsigned ring = 0, icount = 0, tcount = 0;
+      while (true) {
+        const int islot = (int)(icount & 1u);
+        mbar_wait(&q_full[islot], (icount >> 1) & 1u);
+        const int nq = itm[islot].nq;
+        if (nq == 0) break;
+        const int n_tiles = (itm[islot].row1 - itm[islot].row0 + kTile - 1) / kTile;
+        const unsigned char* qsrc = qbuf + (size_t)islot * kblocks * kQBoxBytes;
+        for (int t = 0; t < n_tiles; ++t, ++tcount) {
+          const unsigned set = tcount & 1u;
+          mbar_wait(&acc_empty[set], ((tcount >> 1) & 1u) ^ 1u);  // the filter drained this set
+          tc_fence_after();
+          const uint32_t acc = tmem_base + set * (uint32_t)kTcNQ;
+          for (int kb = 0; kb < kblocks; ++kb, ++ring) {
+            const unsigned s = ring % n_slots;
+            mbar_wait(&full_bar[s], (ring / n_slots) & 1u);
+            tc_fence_after();
+            const uint64_t da = make_kmajor_sw128_desc(slots + (size_t)s * kSlotBytes);
+            const uint64_t db = make_kmajor_sw128_desc(qsrc + kb * kQBoxBytes);
+#pragma unroll
+            for (int k8 = 0; k8 < kTcBK / 8; ++k8)  // UMMA K = 8 tf32 = 32 bytes: +2 in (addr >> 4)
+              tc_mma_tf32(acc, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc,
+                          (kb > 0 || k8 > 0) ? 1u : 0u);
+          }
+          tc_commit(&acc_full[set]);  // the slots are released by the re-rank, not here
+        }
+        ++icount;
+      }
+    }
+    __syncwarp();
+  } else {
+    // =================================== epilogue =========================================
+    const int ew = warp - 2;            // owner index: lists of queries j = ew + kEpiWarps * i
+    const int quarter = warp & 3;       // TMEM lanes this warp may read
+    const int r_local = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int l4 = lane & 3;
+    unsigned ring = 0, icount = 0, tcount = 0;
+    while (true) {
+      const int islot = (int)(icount & 1u);
+      mbar_wait(&q_full[islot], (icount >> 1) & 1u);
+      const TcItem rec = itm[islot];
+      const int nq = rec.nq;
+      if (nq == 0) break;
+      const unsigned char* qsrc = qbuf + (size_t)islot * kblocks * kQBoxBytes;
+
+      WarpTopK<1, int> top[kOwn];
+      float ext[kOwn], qn2[kOwn];
+      int fidx[kOwn];
+#pragma unroll
+      for (int i = 0; i < kOwn; ++i) {
+        const int j = ew + kEpiWarps * i;
+        top[i].init(NLSH_ID_SENTINEL);
+        fidx[i] = -1;
+        ext[i] = neg_inf();
+        qn2[i] = 0.f;
+        if (j < nq) {
+          fidx[i] = a.pairs[rec.pair_base + j];
+          qn2[i] = a.qs_norm[rec.pair_base + j];
+          ext[i] = __ldcg(a.tau_g + fidx[i] / a.p);
+        }
+        if (lane == 0) thr[j] = (j < nq) ? make_thr<METRIC>(ext[i], qn2[i], a.l2_slack) : neg_inf();
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+
+      const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
+      for (int t = 0; t < n_tiles; ++t, ++tcount) {
+        // ------------------------------- filter ------------------------------------------
+        const int row = rec.row0 + t * kTile + r_local;
+        const bool valid = row < rec.row1;
+        int* cn = cnt + (tcount & 1u) * kTcNQ;
+        if (ew == 0) cnt[((tcount + 1u) & 1u) * kTcNQ + lane] = 0;  // the next tile's counters
+        float xn = 0.f;
+        int cid = NLSH_ID_SENTINEL;
+        if (valid) {
+          xn = a.xnorm[row];
+          cid = a.ids[row];
+        }
+        id_s[r_local] = cid;
+        float ra, rb;  // bound = ra * dot + rb
+        if (METRIC == NLSH_METRIC_L2) {
+          ra = -2.0f;
+          rb = (1.0f - kFilterC) * xn;
+        } else {
+          ra = -1.0f / fmaxf(sqrtf(xn), 1e-8f);
+          rb = 0.f;
+        }
+        const unsigned set = tcount & 1u;
+        mbar_wait(&acc_full[set], (tcount >> 1) & 1u);
+        tc_fence_after();
+        uint32_t v0[16], v1[16];
+        tc_ld16_nowait(lane_base + set * (uint32_t)kTcNQ, v0);
+        tc_ld16_nowait(lane_base + set * (uint32_t)kTcNQ + 16u, v1);
+        tc_wait_ld2(v0, v1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[set]);  // TMEM set free for the tile after next
+        unsigned mask = 0;
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const float4 t0 = *reinterpret_cast<const float4*>(thr + j4);
+          const float4 t1 = *reinterpret_cast<const float4*>(thr + 16 + j4);
+          mask |= (fmaf(ra, __uint_as_float(v0[j4 + 0]), rb) <= t0.x ? 1u : 0u) << (j4 + 0);
+          mask |= (fmaf(ra, __uint_as_float(v0[j4 + 1]), rb) <= t0.y ? 1u : 0u) << (j4 + 1);
+          mask |= (fmaf(ra, __uint_as_float(v0[j4 + 2]), rb) <= t0.z ? 1u : 0u) << (j4 + 2);
+          mask |= (fmaf(ra, __uint_as_float(v0[j4 + 3]), rb) <= t0.w ? 1u : 0u) << (j4 + 3);
+          mask |= (fmaf(ra, __uint_as_float(v1[j4 + 0]), rb) <= t1.x ? 1u : 0u) << (16 + j4 + 0);
+          mask |= (fmaf(ra, __uint_as_float(v1[j4 + 1]), rb) <= t1.y ? 1u : 0u) << (16 + j4 + 1);
+          mask |= (fmaf(ra, __uint_as_float(v1[j4 + 2]), rb) <= t1.z ? 1u : 0u) << (16 + j4 + 2);
+          mask |= (fmaf(ra, __uint_as_float(v1[j4 + 3]), rb) <= t1.w ? 1u : 0u) << (16 + j4 + 3);
+        }
+        if (!valid) mask = 0;
+        unsigned any = __reduce_or_sync(NLSH_FULL_MASK, mask);
+        while (any) {  // warp-uniform: bin this warp's survivors of query j
+          const int j = __ffs(any) - 1;
+          any &= any - 1;
+          const bool mine = (mask >> j) & 1u;
+          const unsigned b = __ballot_sync(NLSH_FULL_MASK, mine);
+          int pos = 0;
+          if (lane == 0) pos = atomicAdd(&cn[j], __popc(b));
+          pos = __shfl_sync(NLSH_FULL_MASK, pos, 0);
+          if (mine) qrows[j * kTile + pos + __popc(b & ((1u << lane) - 1u))] = (unsigned char)r_local;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+
+        // ------------------------------- re-rank ------------------------------------------
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const unsigned rr = ring + (unsigned)kb;  // completed long ago: the wait makes the TMA
+          mbar_wait(&full_bar[rr % n_slots], (rr / n_slots) & 1u);  // writes visible to this thread
+        }
+#pragma unroll
+        for (int i = 0; i < kOwn; ++i) {
+          const int j = ew + kEpiWarps * i;
+          const int n = cn[j];
+          if (n > 0) {  // warp-uniform
+            for (int b0 = 0; b0 < n; b0 += 8) {
+              const int sidx = b0 + (lane >> 2);
+              const bool has = sidx < n;
+              const int r = has ? (int)qrows[j * kTile + sidx] : 0;
+              const float dist = exact_distance<METRIC>(slots, ring, n_slots, qsrc, a.d, r, j, l4);
+              const int cand = id_s[r];
+              top[i].offer(dist, cand, has && l4 == 0 && dist <= ext[i], a.k);
+            }
+            if (lane == 0) thr[j] = make_thr<METRIC>(fminf(top[i].tau, ext[i]), qn2[i], a.l2_slack);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          for (int kb = 0; kb < kblocks; ++kb) mbar_arrive(&empty_bar[(ring + (unsigned)kb) % n_slots]);
+        }
+        ring += (unsigned)kblocks;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      }
+
+      // ------------------------------- item done: partial lists ------------------------------
+#pragma unroll
+      for (int i = 0; i < kOwn; ++i) {
+        if (fidx[i] >= 0) {
+          const size_t slot = ((size_t)fidx[i] * a.max_chunks + rec.chunk) * a.k;
+          if (lane < a.k) {
+            a.part_d[slot + lane] = top[i].d[0];
+            a.part_id[slot + lane] = top[i].id[0];
+          }
+          if (lane == 0 && top[i].tau < pos_inf())
+            atomicMin(reinterpret_cast<int*>(a.tau_g + fidx[i] / a.p),
+                      __float_as_int(fmaxf(top[i].tau, 0.f)));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_empty[islot]);
+      ++icount;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc_dealloc(tmem_base, 64);
+}
+
+// qs[i] = qn[pairs[i] / p] (pair order = grouped by bucket), qs_norm[i] = |qs[i]|^2; one warp per pair.
+__global__ void __launch_bounds__(256)
+    gather_pair_queries_kernel(const float* __restrict__ qn, const int* __restrict__ pairs,
+                               const int* __restrict__ n_valid, long long n_pairs, int p, int d_pad,
+                               float* __restrict__ qs, float* __restrict__ qs_norm,
+                               float* __restrict__ tau_g, long long n_queries) {
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gtid < n_queries) tau_g[gtid] = __int_as_float(0x7f800000);
+  const int lane = lane_id();
+  const long long warp = gtid >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  long long nv = *n_valid;
+  if (nv > n_pairs) nv = n_pairs;
+  for (long long i = warp; i < nv; i += n_warps) {
+    const long long q = pairs[i] / p;
+    float ss = 0.f;
+    for (int c = lane * 4; c < d_pad; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(qn + q * d_pad + c);
+      *reinterpret_cast<float4*>(qs + i * d_pad + c) = v;
+      ss = fmaf(v.x, v.x, ss);
+      ss = fmaf(v.y, v.y, ss);
+      ss = fmaf(v.z, v.z, ss);
+      ss = fmaf(v.w, v.w, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(NLSH_FULL_MASK, ss, o);
+    if (lane == 0) qs_norm[i] = ss;
+  }
+}
+
+size_t scan_tc_smem(int kblocks, int n_slots) {
+  return (size_t)n_slots * kSlotBytes + (size_t)2 * kblocks * kQBoxBytes + kTcNQ * kTile +
+         kTile * sizeof(int) + kTcNQ * sizeof(float) + 2 * kTcNQ * sizeof(int) + 2 * sizeof(TcItem) +
+         (2 * kMaxSlots + 8) * sizeof(uint64_t) + 16 + 1024;
+}
+
+}  // namespace
+
+bool nlsh_scan_tc_supported(int d, int k, int metric) {
+  return d >= 1 && (d + 3) / 4 * 4 <= kMaxKBlocks * kTcBK && k <= 32 &&
+         (metric == NLSH_METRIC_L2 || metric == NLSH_METRIC_ANGULAR);
+}
+
+int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, long long n_pairs,
+                         int p, int d_pad, float* qs, float* qs_norm, float* tau_g,
+                         long long n_queries, cudaStream_t st) {
+  long long threads = n_pairs * 32;
+  if (threads < n_queries) threads = n_queries;
+  long long blocks = (threads + 255) / 256;
+  const long long cap = (long long)nlsh_num_sms() * 16;
+  const long long floor_blocks = (n_queries + 255) / 256;
+  if (blocks > cap) blocks = cap;
+  if (blocks < floor_blocks) blocks = floor_blocks;  // every query's tau_g is written by thread gtid
+  if (blocks < 1) blocks = 1;
+  gather_pair_queries_kernel<<<(unsigned)blocks, 256, 0, st>>>(qn, pairs, n_valid, n_pairs, p, d_pad, qs,
+                                                             qs_norm, tau_g, n_queries);
+  return nlsh_check_cuda(nlsh_post_launch(), "gather_pair_queries_kernel launch");
+}
+
+int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {
+  a.kblocks = (a.d_pad + kTcBK - 1) / kTcBK;
+  a.l2_slack = 2.1e-6f * sqrtf((float)a.d);
+  int n_slots = kMaxSlots;
+  while (n_slots > 2 * a.kblocks && scan_tc_smem(a.kblocks, n_slots) > 224 * 1024) --n_slots;
+  if (n_slots < 2 * a.kblocks) n_slots = 2 * a.kblocks;
+  a.n_slots = n_slots;
+  const size_t smem = scan_tc_smem(a.kblocks, n_slots);
+  CUtensorMap map_x, map_q;
+  int rc;
+  if ((rc = tc_make_map(&map_x, a.xs, a.n_rows, a.d_pad, kTile)) != NLSH_OK) return rc;
+  if ((rc = tc_make_map(&map_q, a.qs, a.n_pairs, a.d_pad, kTcNQ)) != NLSH_OK) return rc;
+  const int grid = nlsh_num_sms();
+  if (metric == NLSH_METRIC_L2) {
+    auto kern = scan_tc_kernel<NLSH_METRIC_L2>;
+    NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(a, map_x, map_q);
+  } else {
+    auto kern = scan_tc_kernel<NLSH_METRIC_ANGULAR>;
+    NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(a, map_x, map_q);
+  }
+  return nlsh_check_cuda(nlsh_post_launch(), "scan_tc_kernel launch");
+}

@@ -55,9 +55,9 @@ PROTOTYPES = {
     "nlsh_codes_from_logits": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "nlsh_topp_probes": (ctypes.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "nlsh_build_workspace_bytes": (_sz, [_i64, _i32]),
-    "nlsh_build_csr": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nlsh_build_csr": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nlsh_query_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i64, _i64]),
-    "nlsh_query_scan_topk": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i64,
+    "nlsh_query_scan_topk": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64,
                                             _i64, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _u32,
                                             _vp]),
     "nlsh_knn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
@@ -244,8 +244,9 @@ def padded_dim(d):
     return (d + 3) // 4 * 4
 
 
-def build_csr(codes, n_buckets, x=None):
-    """codes int32 [n] in [0, n_buckets) -> (offsets int32 [B+1], ids int32 [n], x_sorted|None)."""
+def build_csr(codes, n_buckets, x=None, want_sqnorm=False):
+    """codes int32 [n] in [0, n_buckets) -> (offsets int32 [B+1], ids int32 [n], x_sorted|None)
+    [, x_sqnorm fp32 [n] when want_sqnorm: |x_sorted row|^2, the tensor-core scan filter's input]."""
     require_cuda(codes, "codes")
     codes = codes.to(torch.int32).contiguous()
     n = codes.shape[0]
@@ -260,12 +261,19 @@ def build_csr(codes, n_buckets, x=None):
             raise ValueError(f"build_csr: {n} codes for {x.shape[0]} rows")
         d = x.shape[1]
         xs = torch.empty((n, padded_dim(d)), dtype=torch.float32, device=dev)
+    xn = None
+    if want_sqnorm:
+        if xs is None:
+            raise ValueError("build_csr: want_sqnorm needs x")
+        xn = torch.empty((n,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         nbytes = lib().nlsh_build_workspace_bytes(n, n_buckets)
         ws = _workspace(dev, nbytes)
         rc = lib().nlsh_build_csr(_ptr(codes), n, n_buckets, _ptr(x), d, _ptr(offsets), _ptr(ids),
-                                  _ptr(xs), _ptr(ws), ws.numel(), _stream())
+                                  _ptr(xs), _ptr(xn), _ptr(ws), ws.numel(), _stream())
     _check(rc, "nlsh_build_csr")
+    if want_sqnorm:
+        return offsets, ids, xs, xn
     return offsets, ids, xs
 
 
@@ -273,9 +281,10 @@ def build_csr(codes, n_buckets, x=None):
 # query / kNN / merge
 # --------------------------------------------------------------------------------------
 def query_scan_topk(xq, probes, offsets, ids, x_sorted, d, max_bucket_rows, metric, k,
-                    id_offset=0, flags=0, out=None):
+                    id_offset=0, flags=0, out=None, x_sqnorm=None):
     """-> (ids int64 [Q, k], dists fp32 [Q, k], n_cand int32 [Q]); `out` = preallocated
-    contiguous (ids, dists, n_cand) tensors to write into."""
+    contiguous (ids, dists, n_cand) tensors to write into; x_sqnorm (from build_csr) enables the
+    tensor-core filtered scan."""
     xq = _f32c(xq, "query_vectors")
     require_cuda(probes, "probes")
     probes = probes.to(torch.int32).contiguous()
@@ -299,7 +308,8 @@ def query_scan_topk(xq, probes, offsets, ids, x_sorted, d, max_bucket_rows, metr
         nbytes = lib().nlsh_query_workspace_bytes(nq, p, k, d, n_buckets, n_rows, max_bucket_rows)
         ws = _workspace(dev, nbytes)
         rc = lib().nlsh_query_scan_topk(_ptr(xq), nq, d, _ptr(probes), p, _ptr(offsets), n_buckets,
-                                        _ptr(ids), _ptr(x_sorted), n_rows, max_bucket_rows, metric,
+                                        _ptr(ids), _ptr(x_sorted), _ptr(x_sqnorm), n_rows,
+                                        max_bucket_rows, metric,
                                         k, id_offset, _ptr(out_ids), _ptr(out_d), _ptr(out_n),
                                         _ptr(ws), ws.numel(), flags, _stream())
     _check(rc, "nlsh_query_scan_topk")

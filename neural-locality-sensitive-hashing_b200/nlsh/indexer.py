@@ -168,7 +168,8 @@ class Indexer:
         self._dim = d
         codes, _, _ = self._hashing.hash_tensors(x, 1)
         n_buckets = self._hashing.n_buckets
-        self._offsets, self._ids, self._x_sorted = _native.build_csr(codes, n_buckets, x)
+        self._offsets, self._ids, self._x_sorted, self._x_sqnorm = _native.build_csr(
+            codes, n_buckets, x, want_sqnorm=True)
         off = self._offsets.cpu().numpy().astype(np.int64)  # one sync per build
         if int(off[-1]) != n:
             raise ValueError(f"index build dropped {n - int(off[-1])} rows: bucket codes outside "
@@ -213,7 +214,7 @@ class Indexer:
         return _native.query_scan_topk(
             query_vectors, probes, self._offsets, self._ids, self._x_sorted, self._dim,
             self._max_bucket_rows, self._metric, k, id_offset=self._id_offset,
-            flags=self.scan_flags, out=out)
+            flags=self.scan_flags, out=out, x_sqnorm=self._x_sqnorm)
 
     def query(self, query_vectors, k=10, hash_times=10, probes=None) -> List[List[int]]:
         # indexer.py:56-96: returns (List[List[int]] ids by ascending distance, List[int]

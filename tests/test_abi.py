@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     from nlsh import _native
-    assert _native.lib().nlsh_version() == 100
+    assert _native.lib().nlsh_version() == 200
     assert isinstance(_native.last_error(), str)
 
 
@@ -40,10 +40,10 @@ def test_argument_validation_without_gpu():
     # invalid arguments are rejected before any CUDA call is made
     assert L.nlsh_topp_probes(None, 4, 40, _native.HEAD_SIGMOID, 2, None, None) == _native.ERR_INVALID
     assert "hash_size" in _native.last_error()
-    assert L.nlsh_query_scan_topk(None, 1, 8, None, 1, None, 4, None, None, 0, 0, 7, 10, 0, None,
+    assert L.nlsh_query_scan_topk(None, 1, 8, None, 1, None, 4, None, None, None, 0, 0, 7, 10, 0, None,
                                   None, None, None, 0, 0, None) == _native.ERR_INVALID
     assert "metric" in _native.last_error()
-    assert L.nlsh_build_csr(None, -1, 4, None, 0, None, None, None, None, 0, None) == _native.ERR_INVALID
+    assert L.nlsh_build_csr(None, -1, 4, None, 0, None, None, None, None, None, 0, None) == _native.ERR_INVALID
     assert L.nlsh_build_workspace_bytes(1000, 16) > 0
     assert L.nlsh_query_workspace_bytes(100, 4, 10, 128, 256, 10000, 100) > 0
     assert L.nlsh_knn_workspace_bytes(100, 1000, 128, 10) > 0

@@ -103,6 +103,43 @@ def test_query_against_oracle(oracle, n, d, hs, nq, p, k, metric):
     assert (np.diff(np.where(np.isinf(dd), np.float32(3e38), dd), axis=1) >= 0).all()
 
 
+@pytest.mark.parametrize("n,d,hs,nq,p,k,metric,kind", [
+    (200_000, 128, 6, 3000, 4, 10, "l2", "mixture"),     # ~190 queries per bucket: several query groups
+    (200_000, 128, 10, 2000, 8, 10, "l2", "mixture"),    # small buckets (cfg4 / 8-GPU shard shape)
+    (100_000, 100, 8, 1500, 4, 10, "angular", "mixture"),
+    (60_000, 128, 5, 500, 3, 32, "l2", "offset"),        # |x|^2 >> d^2: the filter passes almost everything
+    (60_000, 64, 5, 500, 3, 10, "angular", "offset"),
+    (40_000, 30, 4, 300, 2, 7, "l2", "duplicates"),      # exact ties -> (distance, id) order; d % 4 != 0
+    (40_000, 8, 4, 300, 2, 10, "angular", "duplicates"),
+    (3000, 128, 2, 5000, 2, 10, "l2", "mixture"),        # far more queries than rows per bucket
+])
+def test_tensor_core_filter_is_exact(n, d, hs, nq, p, k, metric, kind):
+    """scan_tc.cu (tcgen05 tf32 GEMM as a filter + exact re-rank) must return bit-for-bit what the
+    fp32 SIMT scan kernel returns: a pair the filter dropped wrongly would show up here."""
+    from encoders import MultiLayerRelu
+    from nlsh.hashings import MultivariateBernoulli
+    from nlsh.indexer import Indexer
+    torch.manual_seed(n + d + hs)
+    X = mixture(n, d, 3 << hs, seed=n)
+    Q = mixture(nq, d, 3 << hs, seed=n) + 0.1 * torch.randn(nq, d, generator=torch.Generator().manual_seed(7))
+    if kind == "offset":
+        X, Q = X + 200.0, Q + 200.0
+    if kind == "duplicates":
+        X[n // 2:] = X[: n - n // 2]
+        Q[: nq // 2] = X[: nq // 2]
+    h = MultivariateBernoulli(MultiLayerRelu(d, [64, 64]), hs, None)
+    h.train_mode(False)
+    idx = Indexer(h, X.cuda(), None, metric=metric)
+    probes = idx.hash_tensors(Q.cuda(), p)
+    ids, dists, ncand = idx.query_tensors(Q.cuda(), k=k, probes=probes)
+    idx.scan_flags = 2  # bit 1: no tensor-core filter
+    ids2, dists2, ncand2 = idx.query_tensors(Q.cuda(), k=k, probes=probes)
+    assert torch.equal(ncand, ncand2)
+    assert torch.equal(ids, ids2), (ids != ids2).sum().item()
+    assert torch.equal(dists, dists2)
+    assert (ids[:, 0] >= 0).all()
+
+
 def test_edge_cases(oracle):
     from encoders import MultiLayerRelu
     from nlsh.hashings import MultivariateBernoulli
