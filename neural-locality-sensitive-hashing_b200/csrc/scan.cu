@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(128)
 template <int KPL>
 __global__ void __launch_bounds__(128)
     merge_partials_kernel(const float* __restrict__ part_d, const int* __restrict__ part_id,
-                          const int* __restrict__ probes, const int* __restrict__ offsets,
+                          const int* __restrict__ row_ids, const int* __restrict__ probes, const int* __restrict__ offsets,
                           int n_buckets, int p, int k, int rchunk, int max_chunks, int dense,
                           int sqrt_scores, long long n_queries, long long id_offset,
                           long long* __restrict__ ids_out,
@@ -848,6 +848,8 @@ __global__ void __launch_bounds__(128)
         if (e < k) {
           cd = part_d[base + e];
           cid = part_id[base + e];
+          // the tensor-core scan stores row indices of x_sorted: map them to ids here
+          if (row_ids != nullptr && cid != NLSH_ID_SENTINEL) cid = row_ids[cid];
         }
         top.offer(cd, cid, cid != NLSH_ID_SENTINEL, k);
       }
@@ -1008,7 +1010,7 @@ int launch_scan_metric(int metric, const ScanArgs& a, const ScanGeom& g, bool as
   }
 }
 
-int launch_merge_partials(const float* part_d, const int* part_id, const int* probes,
+int launch_merge_partials(const float* part_d, const int* part_id, const int* row_ids, const int* probes,
                           const int* offsets, int n_buckets, int p, int k, int rchunk,
                           int max_chunks, int dense, int sqrt_scores, int64_t n_queries,
                           int64_t id_offset,
@@ -1016,15 +1018,15 @@ int launch_merge_partials(const float* part_d, const int* part_id, const int* pr
   const unsigned blocks = (unsigned)((n_queries + 3) / 4);
   long long* ids_ll = reinterpret_cast<long long*>(ids_out);
   if (k <= 32)
-    merge_partials_kernel<1><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
+    merge_partials_kernel<1><<<blocks, 128, 0, st>>>(part_d, part_id, row_ids, probes, offsets, n_buckets, p,
                                                      k, rchunk, max_chunks, dense, sqrt_scores,
                                                      n_queries, id_offset, ids_ll, dists_out, ncand_out);
   else if (k <= 64)
-    merge_partials_kernel<2><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
+    merge_partials_kernel<2><<<blocks, 128, 0, st>>>(part_d, part_id, row_ids, probes, offsets, n_buckets, p,
                                                      k, rchunk, max_chunks, dense, sqrt_scores,
                                                      n_queries, id_offset, ids_ll, dists_out, ncand_out);
   else
-    merge_partials_kernel<4><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
+    merge_partials_kernel<4><<<blocks, 128, 0, st>>>(part_d, part_id, row_ids, probes, offsets, n_buckets, p,
                                                      k, rchunk, max_chunks, dense, sqrt_scores,
                                                      n_queries, id_offset, ids_ll, dists_out, ncand_out);
   return nlsh_check_cuda(nlsh_post_launch(), "merge_partials_kernel launch");
@@ -1179,7 +1181,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   const bool async = (flags & 1u) == 0;
   // tensor-core filtered scan (scan_tc.cu) whenever the index carries the row norms
   const bool use_tc = tc_sized && async && (flags & 2u) == 0 && x_sqnorm != nullptr && n_rows > 0 &&
-                      scan_use_tc(d, k, metric);
+                      (reinterpret_cast<uintptr_t>(x_sqnorm) & 15) == 0 && scan_use_tc(d, k, metric);
   const ScanPolicy pol = use_tc ? pol_tc : pol_simt;
   const ScanGeom geom = scan_geom(d, k, async);
   const long long n_pairs = (long long)n_queries * p;
@@ -1206,12 +1208,12 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
                                                              w.max_tc_items);
     NLSH_CUDA_TRY(nlsh_post_launch());
     int rc = nlsh_scan_tc_prepare(w.qn, w.pairs, w.pair_off + n_buckets, n_pairs, p, geom.d_pad, w.qs,
-                                  w.qs_norm, w.tau_g, n_queries, st);
+                                  w.qs_norm, w.tau_g, n_queries, probes, offsets, x_sorted, n_buckets,
+                                  geom.d, k, metric, st);
     if (rc != NLSH_OK) return rc;
     TcScanArgs t{};
     t.xs = x_sorted;
     t.xnorm = x_sqnorm;
-    t.ids = ids;
     t.qs = w.qs;
     t.qs_norm = w.qs_norm;
     t.pairs = w.pairs;
@@ -1233,7 +1235,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
     rc = nlsh_scan_tc_launch(metric, t, st);
     nlsh_profile_mark(st, false);
     if (rc != NLSH_OK) return rc;
-    return launch_merge_partials(w.part_d, w.part_id, probes, offsets, n_buckets, p, k, pol.rchunk,
+    return launch_merge_partials(w.part_d, w.part_id, ids, probes, offsets, n_buckets, p, k, pol.rchunk,
                                  pol.max_chunks, 0, metric == NLSH_METRIC_L2 ? 1 : 0, n_queries,
                                  id_offset, ids_out, dists_out, ncand_out, st);
   }
@@ -1274,7 +1276,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   int rc = launch_scan_metric(metric, a, geom, async, grid, st);
   nlsh_profile_mark(st, false);
   if (rc != NLSH_OK) return rc;
-  return launch_merge_partials(w.part_d, w.part_id, probes, offsets, n_buckets, p, k, pol.rchunk,
+  return launch_merge_partials(w.part_d, w.part_id, nullptr, probes, offsets, n_buckets, p, k, pol.rchunk,
                                pol.max_chunks, 0, metric == NLSH_METRIC_L2 ? 1 : 0, n_queries,
                                id_offset, ids_out, dists_out, ncand_out, st);
 }
@@ -1363,7 +1365,7 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
     const int rc = nlsh_knn_tc_run(xq, n_queries, xdb, n_rows, d, metric, k, exclude_self ? 1 : 0,
                                    self_offset, scratch, t_d, t_id, st);
     if (rc != NLSH_OK) return rc;
-    return launch_merge_partials(t_d, t_id, nullptr, nullptr, 1, 1, k, 0, n_blocks, 1, 0, n_queries,
+    return launch_merge_partials(t_d, t_id, nullptr, nullptr, nullptr, 1, 1, k, 0, n_blocks, 1, 0, n_queries,
                                  id_offset, ids_out, dists_out, nullptr, st);
   }
   const KnnPlan kp = knn_plan(n_queries, n_rows);
@@ -1424,7 +1426,7 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
     fill_int_kernel<<<(unsigned)((lists + 255) / 256), 256, 0, st>>>(part_id, lists, NLSH_ID_SENTINEL);
     NLSH_CUDA_TRY(nlsh_post_launch());
   }
-  return launch_merge_partials(part_d, part_id, nullptr, nullptr, 1, 1, k, kp.rchunk, kp.n_blocks, 1,
+  return launch_merge_partials(part_d, part_id, nullptr, nullptr, nullptr, 1, 1, k, kp.rchunk, kp.n_blocks, 1,
                                metric == NLSH_METRIC_L2 ? 1 : 0, n_queries, id_offset, ids_out,
                                dists_out, nullptr, st);
 }

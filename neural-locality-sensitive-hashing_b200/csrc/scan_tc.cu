@@ -31,16 +31,25 @@
 // subset of the candidates is such an upper bound, so the merged result does not depend on the
 // order items happen to run in.
 //
-// Roles in a CTA (one persistent CTA per SM, 192 threads):
-//   warp 0 lane 0  producer: owns the work queue (atomic counter), per item TMA-loads the item's
-//                  queries (box 32 rows x 32 fp32 per K block, SWIZZLE_128B) into a 2-deep ring and
-//                  streams row tiles (box 128 rows x 32 fp32) into the slot ring;
-//   warp 1 lane 0  MMA issuer: per tile, per K block 4 x tcgen05.mma M128 N32 K8 into one of two
-//                  TMEM accumulator sets; tcgen05.commit -> acc_full;
-//   warps 2-5      epilogue: (1) filter: thread = row, tcgen05.ld its 32 scores, bound + compare,
-//                  survivors binned per query in shared memory (warp-aggregated atomics);
-//                  (2) re-rank: each warp owns 8 of the item's queries; 4 lanes per survivor compute
-//                  the exact distance from the swizzled tile, WarpTopK::offer inserts.
+// Roles in a CTA (one persistent CTA per SM, 320 threads) - a four-stage pipeline in which no
+// stage waits for the next one to finish a tile:
+//   warp 0         producer: owns the work queue (atomic counter).  Per item the 32 lanes fetch the
+//                  per-query state (flat probe index, |q|^2, tau_g -> initial thresholds) into
+//                  shared memory, lane 0 TMA-loads the item's queries (box 32 rows x 32 fp32 per K
+//                  block, SWIZZLE_128B; 2-deep item ring) and streams the row tiles (box 128 rows x
+//                  32 fp32) into the slot ring;
+//   warp 1 lane 0  MMA issuer: per tile and K block 4 x tcgen05.mma M128 N32 K8 into one of two
+//                  TMEM accumulator sets; tcgen05.commit frees the slot, the last one of a tile
+//                  signals acc_full - shared memory only ever holds tiles in flight;
+//   warps 2-5      filter: thread = row; tcgen05.ld its 32 scores (then the TMEM set is free
+//                  again), bound + compare, survivors appended to the list of the re-rank warp
+//                  that owns the query (warp-aggregated shared-memory atomics; 4-deep list ring);
+//   warps 6-9      re-rank: each warp owns 8 of the item's queries (register-resident sorted
+//                  lists).  4 lanes per survivor re-read the row (an L2 hit: the tile has just
+//                  streamed through) and compute the exact distance, WarpTopK::offer inserts, the
+//                  thresholds in shared memory are lowered for the filter warps (who may be a few
+//                  tiles ahead: stale thresholds only let more pairs through).
+#include <stdlib.h>
 #include <string.h>
 
 #include "scan_tc.cuh"
@@ -48,13 +57,18 @@
 
 namespace {
 
-constexpr int kEpiWarps = 4;
+constexpr int kFilterWarps = 4;                 // one per TMEM lane quarter
+constexpr int kRerankWarps = 4;
 constexpr int kTile = 128;                      // rows per tile = UMMA M
-constexpr int kThreads = 64 + 32 * kEpiWarps;   // 192
-constexpr int kOwn = kTcNQ / kEpiWarps;         // lists per epilogue warp
+constexpr int kThreads = 64 + 32 * (kFilterWarps + kRerankWarps);  // 320
+constexpr int kOwn = kTcNQ / kRerankWarps;      // lists per re-rank warp
+constexpr int kListCap = kOwn * kTile;          // survivors an owner warp can receive per tile
+constexpr int kSurvBufs = 4;                    // survivor-list ring depth (tiles the filter may run ahead)
 constexpr uint32_t kSlotBytes = kTile * kTcBK * sizeof(float);   // 16 KB: one K block of a row tile
 constexpr uint32_t kQBoxBytes = kTcNQ * kTcBK * sizeof(float);   // 4 KB: one K block of the queries
 constexpr int kMaxSlots = 16;
+constexpr int kMetaFloats = kTile + 4;           // a tile's row norms, from the 16-byte boundary below its first row
+constexpr uint32_t kMetaBytes = 640;            // kMetaFloats * 4 rounded up to 128
 constexpr int kMaxKBlocks = 4;                  // d_pad <= 128
 constexpr float kFilterC = 0.001953125f * 1.02f + 4e-5f;  // see header comment
 constexpr float kAngularC = 2.1e-3f;
@@ -75,14 +89,14 @@ __device__ __forceinline__ float make_thr(float eff, float qn2, float l2_slack) 
   return eff - 1.0f + kAngularC;
 }
 
-// Exact distance of row r of the tile to query j of the item, 4 lanes per pair: lane l4 owns the
-// columns = l4 (mod 4) and walks them in ascending order, the columns of a partial last float4
-// (d % 4 != 0) go to lane 0, and the four partial sums are combined as (s0 + s1) + (s2 + s3).
-// That is exactly the summation order of scan.cu::consume_box (packed float2 accumulators over the
-// columns 0,1 / 2,3 of each float4), so both scan kernels produce the same bits for the same
-// (q, x) - the parity tests compare them with torch.equal.  Both operands sit in SWIZZLE_128B
-// boxes: 16-byte chunk c of row r is stored at chunk position c ^ (r & 7).  L2 returns the
-// squared distance (the root is taken in merge_partials_kernel).
+// Exact distance of row r of the tile (shared memory) to query j of the item, 4 lanes per pair:
+// lane l4 owns the columns = l4 (mod 4) and walks them in ascending order, the columns of a
+// partial last float4 (d % 4 != 0) go to lane 0, and the four partial sums are combined as
+// (s0 + s1) + (s2 + s3).  That is exactly the summation order of scan.cu::consume_box (packed
+// float2 accumulators over the columns 0,1 / 2,3 of each float4), so both scan kernels produce
+// the same bits for the same (q, x) - the parity tests compare them with torch.equal.  Both
+// operands sit in SWIZZLE_128B boxes: 16-byte chunk c of row r is stored at chunk position
+// c ^ (r & 7).  L2 returns the squared distance (the root is taken in merge_partials_kernel).
 template <int METRIC>
 __device__ __noinline__ float exact_distance(const unsigned char* slots, unsigned ring, unsigned n_slots,
                                              const unsigned char* qsrc, int d, int r, int j, int l4) {
@@ -143,18 +157,23 @@ __global__ void __launch_bounds__(kThreads, 1)
   unsigned char* base = stc_smem_raw + ((1024u - (smem_u32(stc_smem_raw) & 1023u)) & 1023u);
   unsigned char* slots = base;                                              // [n_slots][16 KB]
   unsigned char* qbuf = slots + (size_t)a.n_slots * kSlotBytes;             // [2][kblocks][4 KB]
-  unsigned char* qrows = qbuf + (size_t)2 * a.kblocks * kQBoxBytes;         // [kTcNQ][kTile] survivor rows
-  int* id_s = reinterpret_cast<int*>(qrows + kTcNQ * kTile);                // [kTile]
-  float* thr = reinterpret_cast<float*>(id_s + kTile);                      // [kTcNQ]
-  int* cnt = reinterpret_cast<int*>(thr + kTcNQ);                           // [2][kTcNQ]
-  TcItem* itm = reinterpret_cast<TcItem*>(cnt + 2 * kTcNQ);                 // [2]
+  unsigned char* meta = qbuf + (size_t)2 * a.kblocks * kQBoxBytes;          // [n_slots][kMetaBytes] row norms
+  uint16_t* surv = reinterpret_cast<uint16_t*>(meta + (size_t)a.n_slots * kMetaBytes);  // [kSurvBufs][kRerankWarps][kListCap]
+  float* thr_s = reinterpret_cast<float*>(surv + kSurvBufs * kRerankWarps * kListCap);      // [2][kTcNQ]
+  float* own_ext = thr_s + 2 * kTcNQ;                                       // [2][kTcNQ]
+  float* own_qn2 = own_ext + 2 * kTcNQ;                                     // [2][kTcNQ]
+  int* own_f = reinterpret_cast<int*>(own_qn2 + 2 * kTcNQ);                 // [2][kTcNQ]
+  int* cnt = own_f + 2 * kTcNQ;                                             // [kSurvBufs][kRerankWarps]
+  TcItem* itm = reinterpret_cast<TcItem*>(cnt + kSurvBufs * kRerankWarps);  // [2]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(itm + 2);                // [kMaxSlots]
   uint64_t* empty_bar = full_bar + kMaxSlots;                               // [kMaxSlots]
   uint64_t* q_full = empty_bar + kMaxSlots;                                 // [2]
   uint64_t* q_empty = q_full + 2;                                           // [2]
   uint64_t* acc_full = q_empty + 2;                                         // [2]
   uint64_t* acc_empty = acc_full + 2;                                       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* surv_full = acc_empty + 2;                                      // [kSurvBufs]
+  uint64_t* surv_empty = surv_full + kSurvBufs;                             // [kSurvBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(surv_empty + kSurvBufs);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -165,17 +184,21 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (tid == 0) {
     for (int s = 0; s < a.n_slots; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kEpiWarps);
+      mbar_init(&empty_bar[s], kRerankWarps);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
-      mbar_init(&q_empty[s], kEpiWarps);
+      mbar_init(&q_empty[s], kRerankWarps);
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], kEpiWarps);
+      mbar_init(&acc_empty[s], kFilterWarps);
+    }
+    for (int s = 0; s < kSurvBufs; ++s) {
+      mbar_init(&surv_full[s], kFilterWarps);
+      mbar_init(&surv_empty[s], kRerankWarps);
     }
     mbar_fence_init();
   }
-  if (tid < 2 * kTcNQ) cnt[tid] = 0;
+  if (tid < kSurvBufs * kRerankWarps) cnt[tid] = 0;
   if (warp == 1) tc_alloc(tmem_slot, 64);  // two accumulator sets of kTcNQ columns
   tc_fence_before();
   __syncthreads();
@@ -184,21 +207,40 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp == 0) {
     // =================================== producer =========================================
-    if (lane == 0) {
-      int total = *a.n_items;
-      if (total > a.max_items) total = a.max_items;
-      unsigned ring = 0, icount = 0;
-      while (true) {
-        const int item = atomicAdd(a.item_counter, 1);
-        const int islot = (int)(icount & 1u);
-        mbar_wait(&q_empty[islot], ((icount >> 1) & 1u) ^ 1u);
-        if (item >= total) {
+    int total = *a.n_items;
+    if (total > a.max_items) total = a.max_items;
+    unsigned ring = 0, icount = 0;
+    while (true) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(a.item_counter, 1);
+      item = __shfl_sync(NLSH_FULL_MASK, item, 0);
+      const int islot = (int)(icount & 1u);
+      mbar_wait(&q_empty[islot], ((icount >> 1) & 1u) ^ 1u);
+      if (item >= total) {
+        if (lane == 0) {
           itm[islot].nq = 0;  // end of work
           mbar_arrive(&q_full[islot]);
-          break;
         }
-        const TcItem rec = a.items[item];
-        itm[islot] = rec;
+        break;
+      }
+      const TcItem rec = a.items[item];
+      {  // lane j: state of the item's query j
+        float th = neg_inf(), ex = neg_inf(), qn = 0.f;
+        int f = -1;
+        if (lane < rec.nq) {
+          f = a.pairs[rec.pair_base + lane];
+          qn = a.qs_norm[rec.pair_base + lane];
+          ex = __ldcg(a.tau_g + f / a.p);
+          th = make_thr<METRIC>(ex, qn, a.l2_slack);
+        }
+        thr_s[islot * kTcNQ + lane] = th;
+        own_ext[islot * kTcNQ + lane] = ex;
+        own_qn2[islot * kTcNQ + lane] = qn;
+        own_f[islot * kTcNQ + lane] = f;
+      }
+      if (lane == 0) itm[islot] = rec;
+      __syncwarp();
+      if (lane == 0) {
         mbar_arrive_expect_tx(&q_full[islot], (unsigned)kblocks * kQBoxBytes);
         unsigned char* qdst = qbuf + (size_t)islot * kblocks * kQBoxBytes;
         for (int kb = 0; kb < kblocks; ++kb)
@@ -209,15 +251,28 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int kb = 0; kb < kblocks; ++kb, ++ring) {
             const unsigned s = ring % n_slots;
             mbar_wait(&empty_bar[s], ((ring / n_slots) & 1u) ^ 1u);
-            // a box is always written in full (rows / columns past the tensor are zero filled)
-            mbar_arrive_expect_tx(&full_bar[s], kSlotBytes);
+            // a box is always written in full (rows / columns past the tensor are zero filled);
+            // the tile's row norms and row ids ride on its first slot
+            // a box is always written in full (rows / columns past the tensor are zero filled).
+            // The tile's row norms ride on its first slot: a plain bulk copy needs a 16-byte aligned
+            // source, so it starts at the 4-row boundary below the tile and stops at the last whole
+            // group of 4 rows of the array (the filter reads the <= 3 rows after that directly).
+            unsigned extra = 0;
+            const long long m0 = trow0 & ~3ll;
+            if (kb == 0) {
+              long long avail = (a.n_rows & ~3ll) - m0;
+              if (avail > kMetaFloats) avail = kMetaFloats;
+              if (avail > 0) extra = (unsigned)avail * 4u;
+            }
+            mbar_arrive_expect_tx(&full_bar[s], kSlotBytes + extra);
             tma_load_2d(slots + (size_t)s * kSlotBytes, &map_x, kb * kTcBK, trow0, &full_bar[s]);
+            if (extra) bulk_g2s(meta + (size_t)s * kMetaBytes, a.xnorm + m0, extra, &full_bar[s]);
           }
         }
-        ++icount;
       }
+      __syncwarp();
+      ++icount;
     }
-    __syncwarp();
   } else if (warp == 1) {
     // =================================== MMA issuer =======================================
     if (lane == 0) {
@@ -246,69 +301,33 @@ __global__ void __launch_bounds__(kThreads, 1)
               tc_mma_tf32(acc, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc,
                           (kb > 0 || k8 > 0) ? 1u : 0u);
           }
-          tc_commit(&acc_full[set]);  // the slots are released by the re-rank, not here
+          tc_commit(&acc_full[set]);  // the slots are released by the re-rank warps, not here
         }
         ++icount;
       }
     }
     __syncwarp();
-  } else {
-    // =================================== epilogue =========================================
-    const int ew = warp - 2;            // owner index: lists of queries j = ew + kEpiWarps * i
-    const int quarter = warp & 3;       // TMEM lanes this warp may read
+  } else if (warp < 2 + kFilterWarps) {
+    // =================================== filter ============================================
+    const int quarter = warp & 3;  // TMEM lanes this warp may read
     const int r_local = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int l4 = lane & 3;
     unsigned ring = 0, icount = 0, tcount = 0;
     while (true) {
       const int islot = (int)(icount & 1u);
       mbar_wait(&q_full[islot], (icount >> 1) & 1u);
       const TcItem rec = itm[islot];
-      const int nq = rec.nq;
-      if (nq == 0) break;
-      const unsigned char* qsrc = qbuf + (size_t)islot * kblocks * kQBoxBytes;
-
-      WarpTopK<1, int> top[kOwn];
-      float ext[kOwn], qn2[kOwn];
-      int fidx[kOwn];
-#pragma unroll
-      for (int i = 0; i < kOwn; ++i) {
-        const int j = ew + kEpiWarps * i;
-        top[i].init(NLSH_ID_SENTINEL);
-        fidx[i] = -1;
-        ext[i] = neg_inf();
-        qn2[i] = 0.f;
-        if (j < nq) {
-          fidx[i] = a.pairs[rec.pair_base + j];
-          qn2[i] = a.qs_norm[rec.pair_base + j];
-          ext[i] = __ldcg(a.tau_g + fidx[i] / a.p);
-        }
-        if (lane == 0) thr[j] = (j < nq) ? make_thr<METRIC>(ext[i], qn2[i], a.l2_slack) : neg_inf();
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-
+      if (rec.nq == 0) break;
+      const float* th = thr_s + islot * kTcNQ;
       const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
       for (int t = 0; t < n_tiles; ++t, ++tcount) {
-        // ------------------------------- filter ------------------------------------------
         const int row = rec.row0 + t * kTile + r_local;
         const bool valid = row < rec.row1;
-        int* cn = cnt + (tcount & 1u) * kTcNQ;
-        if (ew == 0) cnt[((tcount + 1u) & 1u) * kTcNQ + lane] = 0;  // the next tile's counters
-        float xn = 0.f;
-        int cid = NLSH_ID_SENTINEL;
-        if (valid) {
-          xn = a.xnorm[row];
-          cid = a.ids[row];
-        }
-        id_s[r_local] = cid;
-        float ra, rb;  // bound = ra * dot + rb
-        if (METRIC == NLSH_METRIC_L2) {
-          ra = -2.0f;
-          rb = (1.0f - kFilterC) * xn;
-        } else {
-          ra = -1.0f / fmaxf(sqrtf(xn), 1e-8f);
-          rb = 0.f;
-        }
+        const unsigned s0 = ring % n_slots;  // the tile's first slot carries its row norms
+        mbar_wait(&full_bar[s0], (ring / n_slots) & 1u);
+        float xn = reinterpret_cast<const float*>(meta + (size_t)s0 * kMetaBytes)[((rec.row0 + t * kTile) & 3) + r_local];
+        if (row >= (a.n_rows & ~3ll)) xn = valid ? a.xnorm[row] : 0.f;
+        ring += (unsigned)kblocks;
         const unsigned set = tcount & 1u;
         mbar_wait(&acc_full[set], (tcount >> 1) & 1u);
         tc_fence_after();
@@ -319,11 +338,19 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[set]);  // TMEM set free for the tile after next
+        float ra, rb;  // bound = ra * dot + rb
+        if (METRIC == NLSH_METRIC_L2) {
+          ra = -2.0f;
+          rb = (1.0f - kFilterC) * xn;
+        } else {
+          ra = -1.0f / fmaxf(sqrtf(xn), 1e-8f);
+          rb = 0.f;
+        }
         unsigned mask = 0;
 #pragma unroll
         for (int j4 = 0; j4 < 16; j4 += 4) {
-          const float4 t0 = *reinterpret_cast<const float4*>(thr + j4);
-          const float4 t1 = *reinterpret_cast<const float4*>(thr + 16 + j4);
+          const float4 t0 = *reinterpret_cast<const float4*>(th + j4);
+          const float4 t1 = *reinterpret_cast<const float4*>(th + 16 + j4);
           mask |= (fmaf(ra, __uint_as_float(v0[j4 + 0]), rb) <= t0.x ? 1u : 0u) << (j4 + 0);
           mask |= (fmaf(ra, __uint_as_float(v0[j4 + 1]), rb) <= t0.y ? 1u : 0u) << (j4 + 1);
           mask |= (fmaf(ra, __uint_as_float(v0[j4 + 2]), rb) <= t0.z ? 1u : 0u) << (j4 + 2);
@@ -334,46 +361,93 @@ __global__ void __launch_bounds__(kThreads, 1)
           mask |= (fmaf(ra, __uint_as_float(v1[j4 + 3]), rb) <= t1.w ? 1u : 0u) << (16 + j4 + 3);
         }
         if (!valid) mask = 0;
+        const unsigned sb = tcount % kSurvBufs, use = tcount / kSurvBufs;
+        mbar_wait(&surv_empty[sb], (use & 1u) ^ 1u);  // the re-rank warps are done with this buffer
+        int* cn = cnt + sb * kRerankWarps;
+        uint16_t* sv = surv + (size_t)sb * kRerankWarps * kListCap;
         unsigned any = __reduce_or_sync(NLSH_FULL_MASK, mask);
-        while (any) {  // warp-uniform: bin this warp's survivors of query j
+        while (any) {  // warp-uniform: hand this warp's survivors of query j to j's owner warp
           const int j = __ffs(any) - 1;
           any &= any - 1;
+          const int owner = j & (kRerankWarps - 1);
           const bool mine = (mask >> j) & 1u;
           const unsigned b = __ballot_sync(NLSH_FULL_MASK, mine);
           int pos = 0;
-          if (lane == 0) pos = atomicAdd(&cn[j], __popc(b));
+          if (lane == 0) pos = atomicAdd(&cn[owner], __popc(b));
           pos = __shfl_sync(NLSH_FULL_MASK, pos, 0);
-          if (mine) qrows[j * kTile + pos + __popc(b & ((1u << lane) - 1u))] = (unsigned char)r_local;
+          if (mine)
+            sv[owner * kListCap + pos + __popc(b & ((1u << lane) - 1u))] = (uint16_t)((j << 8) | r_local);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&surv_full[sb]);
+      }
+      ++icount;
+    }
+  } else {
+    // =================================== re-rank ===========================================
+    const int rw = warp - 2 - kFilterWarps;  // owner index: lists of queries j = rw + kRerankWarps * i
+    const int l4 = lane & 3;
+    unsigned ring = 0, icount = 0, tcount = 0;
+    while (true) {
+      const int islot = (int)(icount & 1u);
+      mbar_wait(&q_full[islot], (icount >> 1) & 1u);
+      const TcItem rec = itm[islot];
+      if (rec.nq == 0) break;
+      const unsigned char* qsrc = qbuf + (size_t)islot * kblocks * kQBoxBytes;
+      float* th = thr_s + islot * kTcNQ;
 
-        // ------------------------------- re-rank ------------------------------------------
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const unsigned rr = ring + (unsigned)kb;  // completed long ago: the wait makes the TMA
-          mbar_wait(&full_bar[rr % n_slots], (rr / n_slots) & 1u);  // writes visible to this thread
-        }
+      WarpTopK<1, int> top[kOwn];
+      float ext[kOwn], qn2[kOwn];
+      int fidx[kOwn];
 #pragma unroll
-        for (int i = 0; i < kOwn; ++i) {
-          const int j = ew + kEpiWarps * i;
-          const int n = cn[j];
-          if (n > 0) {  // warp-uniform
-            for (int b0 = 0; b0 < n; b0 += 8) {
-              const int sidx = b0 + (lane >> 2);
-              const bool has = sidx < n;
-              const int r = has ? (int)qrows[j * kTile + sidx] : 0;
-              const float dist = exact_distance<METRIC>(slots, ring, n_slots, qsrc, a.d, r, j, l4);
-              const int cand = id_s[r];
-              top[i].offer(dist, cand, has && l4 == 0 && dist <= ext[i], a.k);
-            }
-            if (lane == 0) thr[j] = make_thr<METRIC>(fminf(top[i].tau, ext[i]), qn2[i], a.l2_slack);
+      for (int i = 0; i < kOwn; ++i) {
+        const int j = rw + kRerankWarps * i;
+        top[i].init(NLSH_ID_SENTINEL);
+        fidx[i] = own_f[islot * kTcNQ + j];
+        ext[i] = own_ext[islot * kTcNQ + j];
+        qn2[i] = own_qn2[islot * kTcNQ + j];
+      }
+
+      const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
+      for (int t = 0; t < n_tiles; ++t, ++tcount) {
+        const unsigned sb = tcount % kSurvBufs, use = tcount / kSurvBufs;
+        mbar_wait(&surv_full[sb], use & 1u);
+        int* cn = cnt + sb * kRerankWarps;
+        const int n = cn[rw];
+        if (n > 0) {  // warp-uniform
+          for (int kb = 0; kb < kblocks; ++kb) {
+            const unsigned rr = ring + (unsigned)kb;  // completed long ago: the wait makes the TMA
+            mbar_wait(&full_bar[rr % n_slots], (rr / n_slots) & 1u);  // writes visible to this thread
+          }
+          const uint16_t* mine_sv = surv + ((size_t)sb * kRerankWarps + rw) * kListCap;
+          const int trow0 = rec.row0 + t * kTile;
+          for (int b0 = 0; b0 < n; b0 += 8) {
+            const int sidx = b0 + (lane >> 2);
+            const bool has = sidx < n;
+            const int e = has ? (int)mine_sv[sidx] : 0;  // (query 0, row 0 of the tile): valid addresses
+            const int j = e >> 8, r = e & 255;
+            // lists carry the ROW index: inside a bucket rows ascend with the ids (nlsh_build_csr), so
+            // (distance, row) orders like (distance, id); merge_partials_kernel maps rows to ids
+            const int cand = trow0 + r;
+            const float dist = exact_distance<METRIC>(slots, ring, n_slots, qsrc, a.d, r, j, l4);
+            const int own = j >> 2;  // j = rw + kRerankWarps * own
+#pragma unroll
+            for (int i = 0; i < kOwn; ++i)
+              top[i].offer(dist, cand, has && l4 == 0 && own == i && dist <= ext[i], a.k);
+          }
+          if (lane == 0) {
+            cn[rw] = 0;  // before the buffer is handed back
+#pragma unroll
+            for (int i = 0; i < kOwn; ++i)
+              th[rw + kRerankWarps * i] = make_thr<METRIC>(fminf(top[i].tau, ext[i]), qn2[i], a.l2_slack);
           }
         }
         __syncwarp();
         if (lane == 0) {
+          mbar_arrive(&surv_empty[sb]);
           for (int kb = 0; kb < kblocks; ++kb) mbar_arrive(&empty_bar[(ring + (unsigned)kb) % n_slots]);
         }
         ring += (unsigned)kblocks;
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
 
       // ------------------------------- item done: partial lists ------------------------------
@@ -431,10 +505,72 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Initial tau_g: the exact k-th best distance of each query among the first kSeedRows rows of its
+// first probed bucket (one warp per query, one or two rows per lane).  Any k candidates bound the
+// final k-th distance from above, so this is a valid threshold from the very first tile; without it
+// every (query, bucket) list starts empty and the first 128-row tile of each bucket survives the
+// filter whole.  The bound is inflated by a few ulps-of-the-sum because the re-rank sums the same
+// terms in a different order.
+constexpr int kSeedRows = 64;
+
+template <int METRIC>
+__global__ void __launch_bounds__(128)
+    seed_tau_kernel(const float* __restrict__ qn, const int* __restrict__ probes,
+                    const int* __restrict__ offsets, const float* __restrict__ xs, int n_buckets, int p,
+                    int d, int d_pad, int k, long long n_queries, float* __restrict__ tau_g) {
+  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n_queries) return;
+  const int lane = lane_id();
+  const int b = probes[q * p];
+  if (b < 0 || b >= n_buckets) return;
+  const int r0 = offsets[b];
+  int n = offsets[b + 1] - r0;
+  if (n > kSeedRows) n = kSeedRows;
+  if (n < k) return;
+  const float* qv = qn + q * d_pad;
+  float dist[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = lane + 32 * h;
+    float acc = 0.f, xx = 0.f;
+    if (r < n) {
+      const float* xr = xs + (size_t)(r0 + r) * d_pad;
+      for (int c = 0; c < d; c += 4) {
+        const float4 x4 = *reinterpret_cast<const float4*>(xr + c);
+        const float4 q4 = *reinterpret_cast<const float4*>(qv + c);
+        const float xa[4] = {x4.x, x4.y, x4.z, x4.w};
+        const float qa[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (c + e < d) {
+            if (METRIC == NLSH_METRIC_L2) {
+              const float t = (qa[e] - xa[e]) + 1e-6f;
+              acc = fmaf(t, t, acc);
+            } else {
+              acc = fmaf(qa[e], xa[e], acc);
+              xx = fmaf(xa[e], xa[e], xx);
+            }
+          }
+        }
+      }
+    }
+    dist[h] = METRIC == NLSH_METRIC_L2 ? acc : 1.0f - acc / fmaxf(sqrtf(xx), 1e-8f);
+  }
+  WarpTopK<1, int> top;
+  top.init(NLSH_ID_SENTINEL);
+  top.seed32(dist[0], lane, lane < n, NLSH_ID_SENTINEL, k);
+  top.offer(dist[1], lane + 32, lane + 32 < n, k);
+  if (lane == 0 && top.tau < pos_inf()) {
+    const float t = top.tau;
+    tau_g[q] = METRIC == NLSH_METRIC_L2 ? t * 1.00002f + 1e-30f : t + 4e-6f + 2e-5f * fabsf(t);
+  }
+}
+
 size_t scan_tc_smem(int kblocks, int n_slots) {
-  return (size_t)n_slots * kSlotBytes + (size_t)2 * kblocks * kQBoxBytes + kTcNQ * kTile +
-         kTile * sizeof(int) + kTcNQ * sizeof(float) + 2 * kTcNQ * sizeof(int) + 2 * sizeof(TcItem) +
-         (2 * kMaxSlots + 8) * sizeof(uint64_t) + 16 + 1024;
+  return (size_t)n_slots * (kSlotBytes + kMetaBytes) + (size_t)2 * kblocks * kQBoxBytes +
+         kSurvBufs * kRerankWarps * kListCap * sizeof(uint16_t) + 8 * kTcNQ * sizeof(float) +
+         kSurvBufs * kRerankWarps * sizeof(int) + 2 * sizeof(TcItem) +
+         (2 * kMaxSlots + 8 + 2 * kSurvBufs) * sizeof(uint64_t) + 16 + 1024;
 }
 
 }  // namespace
@@ -446,7 +582,8 @@ bool nlsh_scan_tc_supported(int d, int k, int metric) {
 
 int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, long long n_pairs,
                          int p, int d_pad, float* qs, float* qs_norm, float* tau_g,
-                         long long n_queries, cudaStream_t st) {
+                         long long n_queries, const int* probes, const int* offsets, const float* xs,
+                         int n_buckets, int d, int k, int metric, cudaStream_t st) {
   long long threads = n_pairs * 32;
   if (threads < n_queries) threads = n_queries;
   long long blocks = (threads + 255) / 256;
@@ -457,7 +594,17 @@ int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, 
   if (blocks < 1) blocks = 1;
   gather_pair_queries_kernel<<<(unsigned)blocks, 256, 0, st>>>(qn, pairs, n_valid, n_pairs, p, d_pad, qs,
                                                              qs_norm, tau_g, n_queries);
-  return nlsh_check_cuda(nlsh_post_launch(), "gather_pair_queries_kernel launch");
+  NLSH_CUDA_TRY(nlsh_post_launch());
+  const char* env = getenv("NLSH_SCAN_SEED");  // NLSH_SCAN_SEED=0: no seeding (A/B runs)
+  if (env != nullptr && env[0] == '0') return NLSH_OK;
+  const unsigned sb = (unsigned)((n_queries + 3) / 4);
+  if (metric == NLSH_METRIC_L2)
+    seed_tau_kernel<NLSH_METRIC_L2><<<sb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad, k,
+                                                       n_queries, tau_g);
+  else
+    seed_tau_kernel<NLSH_METRIC_ANGULAR><<<sb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad,
+                                                            k, n_queries, tau_g);
+  return nlsh_check_cuda(nlsh_post_launch(), "seed_tau_kernel launch");
 }
 
 int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {

@@ -19,7 +19,6 @@ static_assert(sizeof(TcItem) == 32, "TcItem must be 32 bytes");
 struct TcScanArgs {
   const float* xs;       // [n_rows, d_pad] bucket-contiguous vectors
   const float* xnorm;    // [n_rows] |x|^2 of each row of xs
-  const int* ids;        // [n_rows]
   const float* qs;       // [n_pairs, d_pad] query vectors in pair order (pre-normalised for ANGULAR)
   const float* qs_norm;  // [n_pairs] |q|^2 of each row of qs
   const int* pairs;      // [n_pairs] flat probe index f = q * p + slot of each pair
@@ -29,7 +28,7 @@ struct TcScanArgs {
   int* item_counter;
   float* tau_g;          // [n_queries] best known upper bound of each query's final k-th distance
   float* part_d;         // [n_queries * p, max_chunks, k]
-  int* part_id;
+  int* part_id;          // ROW indices into xs (merge_partials_kernel maps them through ids)
   long long n_rows;
   long long n_pairs;
   int p, k, d, d_pad, kblocks, max_chunks, n_slots;
@@ -37,8 +36,10 @@ struct TcScanArgs {
 };
 
 bool nlsh_scan_tc_supported(int d, int k, int metric);
-// qs[i] = qn[pairs[i] / p], qs_norm[i] = |qs[i]|^2 for i < *n_valid; tau_g[:] = +inf
+// qs[i] = qn[pairs[i] / p], qs_norm[i] = |qs[i]|^2 for i < *n_valid; tau_g[q] = the exact k-th best
+// distance of query q among the first rows of its first probed bucket (+inf when it has < k rows)
 int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, long long n_pairs,
                          int p, int d_pad, float* qs, float* qs_norm, float* tau_g,
-                         long long n_queries, cudaStream_t st);
+                         long long n_queries, const int* probes, const int* offsets, const float* xs,
+                         int n_buckets, int d, int k, int metric, cudaStream_t st);
 int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st);
