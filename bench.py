@@ -308,8 +308,10 @@ def run_b200(args):
     # ---- scan-kernel roofline: CUDA events around the kernel inside the library --------------
     _native.profile_enable(True)
     prof_steps = min(max(args.steps, 3), 200)
+    torch.cuda.nvtx.range_push("nlsh_steps")  # ncu --nvtx --nvtx-include "nlsh_steps/": one step's launches
     for _ in range(prof_steps):
         _, _, ncand_local = index.local.query_tensors(Q, k=k, hash_times=p_used)
+    torch.cuda.nvtx.range_pop()
     scan_ms = _native.profile_read()
     # the same kernel where no bucket tile is shared between queries (about one probing query
     # per two buckets): every candidate byte has to come from HBM, so this is the figure to
@@ -343,6 +345,9 @@ def run_b200(args):
         traffic = rec["dram_bytes_per_launch"] if rec else None
     qps = nq * args.steps / (ms * 1e-3)
     e2e_qps = nq * args.steps / (e2e_ms * 1e-3)
+    scan_impl = _native.scan_impl(d, k, index.local._metric, index.local._x_sqnorm is not None)
+    scan_kernel_name = ("scan_tc_kernel (tcgen05 tf32 filter + exact fp32 re-rank + top-k)" if scan_impl == 1
+                        else "scan_kernel (fp32 SIMT candidate scan + top-k)")
     line = {
         "metric": "QPS at recall@10>=0.9", "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -362,7 +367,7 @@ def run_b200(args):
                 if hasattr(run_query, "kernels_per_call") else "ShardedIndexer.query_tensors, pinned host in/out"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "scan_kernel (candidate scan + top-k)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": scan_kernel_name, "achieved": achieved,
                      "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": scan_avg_ms,

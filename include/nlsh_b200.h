@@ -164,6 +164,10 @@ int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t d, const in
                          float* dists_out, int32_t* ncand_out, void* workspace,
                          size_t workspace_bytes, uint32_t flags, void* stream);
 
+/* Which kernel nlsh_query_scan_topk runs for (d, k, metric) with / without x_sqnorm and default
+ * flags: 1 = tensor-core filtered scan (scan_tc.cu), 0 = fp32 SIMT scan (scan.cu). */
+int nlsh_query_scan_impl(int32_t d, int32_t k, int32_t metric, int32_t has_sqnorm);
+
 /* ---------------------------------------------------------------------------------------
  * Brute-force kNN (ground truth / training labels).
  * Replaces self_get_knn_pt (precompute.py:57-67) with distance_func = _l2

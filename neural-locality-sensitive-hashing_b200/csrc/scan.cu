@@ -1132,6 +1132,10 @@ bool scan_use_tc(int d, int k, int metric) {
 }
 }  // namespace
 
+extern "C" int nlsh_query_scan_impl(int32_t d, int32_t k, int32_t metric, int32_t has_sqnorm) {
+  return (has_sqnorm && scan_use_tc(d, k, metric)) ? 1 : 0;
+}
+
 extern "C" size_t nlsh_query_workspace_bytes(int64_t n_queries, int32_t p, int32_t k, int32_t d,
                                              int32_t n_buckets, int64_t n_rows,
                                              int64_t max_bucket_rows) {
@@ -1221,6 +1225,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
     t.n_items = w.item_off + n_buckets;
     t.max_items = w.max_tc_items;
     t.item_counter = w.counter;
+    t.stats = getenv("NLSH_TC_STATS") ? reinterpret_cast<unsigned long long*>(w.counter + 2) : nullptr;
     t.tau_g = w.tau_g;
     t.part_d = w.part_d;
     t.part_id = w.part_id;

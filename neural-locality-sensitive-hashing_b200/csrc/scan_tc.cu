@@ -31,7 +31,7 @@
 // subset of the candidates is such an upper bound, so the merged result does not depend on the
 // order items happen to run in.
 //
-// Roles in a CTA (one persistent CTA per SM, 320 threads) - a four-stage pipeline in which no
+// Roles in a CTA (one persistent CTA per SM, 448 threads) - a four-stage pipeline in which no
 // stage waits for the next one to finish a tile:
 //   warp 0         producer: owns the work queue (atomic counter).  Per item the 32 lanes fetch the
 //                  per-query state (flat probe index, |q|^2, tau_g -> initial thresholds) into
@@ -44,7 +44,7 @@
 //   warps 2-5      filter: thread = row; tcgen05.ld its 32 scores (then the TMEM set is free
 //                  again), bound + compare, survivors appended to the list of the re-rank warp
 //                  that owns the query (warp-aggregated shared-memory atomics; 4-deep list ring);
-//   warps 6-9      re-rank: each warp owns 8 of the item's queries (register-resident sorted
+//   warps 6-13     re-rank: each warp owns 4 of the item's queries (register-resident sorted
 //                  lists).  4 lanes per survivor re-read the row (an L2 hit: the tile has just
 //                  streamed through) and compute the exact distance, WarpTopK::offer inserts, the
 //                  thresholds in shared memory are lowered for the filter warps (who may be a few
@@ -57,8 +57,15 @@
 
 namespace {
 
+#ifdef NLSH_TC_SUSPEND_WAIT
+#define MBAR_WAIT mbar_wait
+#else
+#define MBAR_WAIT mbar_wait_poll
+#endif
+
 constexpr int kFilterWarps = 4;                 // one per TMEM lane quarter
-constexpr int kRerankWarps = 4;
+constexpr int kRerankWarps = 8;                 // two per scheduler: their latencies overlap
+constexpr int kRerankShift = 3;                 // log2(kRerankWarps)
 constexpr int kTile = 128;                      // rows per tile = UMMA M
 constexpr int kThreads = 64 + 32 * (kFilterWarps + kRerankWarps);  // 320
 constexpr int kOwn = kTcNQ / kRerankWarps;      // lists per re-rank warp
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (lane == 0) item = atomicAdd(a.item_counter, 1);
       item = __shfl_sync(NLSH_FULL_MASK, item, 0);
       const int islot = (int)(icount & 1u);
-      mbar_wait(&q_empty[islot], ((icount >> 1) & 1u) ^ 1u);
+      MBAR_WAIT(&q_empty[islot], ((icount >> 1) & 1u) ^ 1u);
       if (item >= total) {
         if (lane == 0) {
           itm[islot].nq = 0;  // end of work
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int trow0 = rec.row0 + t * kTile;
           for (int kb = 0; kb < kblocks; ++kb, ++ring) {
             const unsigned s = ring % n_slots;
-            mbar_wait(&empty_bar[s], ((ring / n_slots) & 1u) ^ 1u);
+            MBAR_WAIT(&empty_bar[s], ((ring / n_slots) & 1u) ^ 1u);
             // a box is always written in full (rows / columns past the tensor are zero filled);
             // the tile's row norms and row ids ride on its first slot
             // a box is always written in full (rows / columns past the tensor are zero filled).
@@ -280,19 +287,19 @@ __global__ void __launch_bounds__(kThreads, 1)
       unsigned ring = 0, icount = 0, tcount = 0;
       while (true) {
         const int islot = (int)(icount & 1u);
-        mbar_wait(&q_full[islot], (icount >> 1) & 1u);
+        MBAR_WAIT(&q_full[islot], (icount >> 1) & 1u);
         const int nq = itm[islot].nq;
         if (nq == 0) break;
         const int n_tiles = (itm[islot].row1 - itm[islot].row0 + kTile - 1) / kTile;
         const unsigned char* qsrc = qbuf + (size_t)islot * kblocks * kQBoxBytes;
         for (int t = 0; t < n_tiles; ++t, ++tcount) {
           const unsigned set = tcount & 1u;
-          mbar_wait(&acc_empty[set], ((tcount >> 1) & 1u) ^ 1u);  // the filter drained this set
+          MBAR_WAIT(&acc_empty[set], ((tcount >> 1) & 1u) ^ 1u);  // the filter drained this set
           tc_fence_after();
           const uint32_t acc = tmem_base + set * (uint32_t)kTcNQ;
           for (int kb = 0; kb < kblocks; ++kb, ++ring) {
             const unsigned s = ring % n_slots;
-            mbar_wait(&full_bar[s], (ring / n_slots) & 1u);
+            MBAR_WAIT(&full_bar[s], (ring / n_slots) & 1u);
             tc_fence_after();
             const uint64_t da = make_kmajor_sw128_desc(slots + (size_t)s * kSlotBytes);
             const uint64_t db = make_kmajor_sw128_desc(qsrc + kb * kQBoxBytes);
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     unsigned ring = 0, icount = 0, tcount = 0;
     while (true) {
       const int islot = (int)(icount & 1u);
-      mbar_wait(&q_full[islot], (icount >> 1) & 1u);
+      MBAR_WAIT(&q_full[islot], (icount >> 1) & 1u);
       const TcItem rec = itm[islot];
       if (rec.nq == 0) break;
       const float* th = thr_s + islot * kTcNQ;
@@ -324,12 +331,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int row = rec.row0 + t * kTile + r_local;
         const bool valid = row < rec.row1;
         const unsigned s0 = ring % n_slots;  // the tile's first slot carries its row norms
-        mbar_wait(&full_bar[s0], (ring / n_slots) & 1u);
+        MBAR_WAIT(&full_bar[s0], (ring / n_slots) & 1u);
         float xn = reinterpret_cast<const float*>(meta + (size_t)s0 * kMetaBytes)[((rec.row0 + t * kTile) & 3) + r_local];
         if (row >= (a.n_rows & ~3ll)) xn = valid ? a.xnorm[row] : 0.f;
         ring += (unsigned)kblocks;
         const unsigned set = tcount & 1u;
-        mbar_wait(&acc_full[set], (tcount >> 1) & 1u);
+        MBAR_WAIT(&acc_full[set], (tcount >> 1) & 1u);
         tc_fence_after();
         uint32_t v0[16], v1[16];
         tc_ld16_nowait(lane_base + set * (uint32_t)kTcNQ, v0);
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         if (!valid) mask = 0;
         const unsigned sb = tcount % kSurvBufs, use = tcount / kSurvBufs;
-        mbar_wait(&surv_empty[sb], (use & 1u) ^ 1u);  // the re-rank warps are done with this buffer
+        MBAR_WAIT(&surv_empty[sb], (use & 1u) ^ 1u);  // the re-rank warps are done with this buffer
         int* cn = cnt + sb * kRerankWarps;
         uint16_t* sv = surv + (size_t)sb * kRerankWarps * kListCap;
         unsigned any = __reduce_or_sync(NLSH_FULL_MASK, mask);
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     unsigned ring = 0, icount = 0, tcount = 0;
     while (true) {
       const int islot = (int)(icount & 1u);
-      mbar_wait(&q_full[islot], (icount >> 1) & 1u);
+      MBAR_WAIT(&q_full[islot], (icount >> 1) & 1u);
       const TcItem rec = itm[islot];
       if (rec.nq == 0) break;
       const unsigned char* qsrc = qbuf + (size_t)islot * kblocks * kQBoxBytes;
@@ -411,13 +418,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
       for (int t = 0; t < n_tiles; ++t, ++tcount) {
         const unsigned sb = tcount % kSurvBufs, use = tcount / kSurvBufs;
-        mbar_wait(&surv_full[sb], use & 1u);
+        MBAR_WAIT(&surv_full[sb], use & 1u);
         int* cn = cnt + sb * kRerankWarps;
         const int n = cn[rw];
         if (n > 0) {  // warp-uniform
           for (int kb = 0; kb < kblocks; ++kb) {
             const unsigned rr = ring + (unsigned)kb;  // completed long ago: the wait makes the TMA
-            mbar_wait(&full_bar[rr % n_slots], (rr / n_slots) & 1u);  // writes visible to this thread
+            MBAR_WAIT(&full_bar[rr % n_slots], (rr / n_slots) & 1u);  // writes visible to this thread
           }
           const uint16_t* mine_sv = surv + ((size_t)sb * kRerankWarps + rw) * kListCap;
           const int trow0 = rec.row0 + t * kTile;
@@ -430,12 +437,16 @@ __global__ void __launch_bounds__(kThreads, 1)
             // (distance, row) orders like (distance, id); merge_partials_kernel maps rows to ids
             const int cand = trow0 + r;
             const float dist = exact_distance<METRIC>(slots, ring, n_slots, qsrc, a.d, r, j, l4);
-            const int own = j >> 2;  // j = rw + kRerankWarps * own
+            const int own = j >> kRerankShift;  // j = rw + kRerankWarps * own
 #pragma unroll
             for (int i = 0; i < kOwn; ++i)
               top[i].offer(dist, cand, has && l4 == 0 && own == i && dist <= ext[i], a.k);
           }
           if (lane == 0) {
+            if (a.stats != nullptr) {  // debug counters: survivors, batches
+              atomicAdd(a.stats, (unsigned long long)n);
+              atomicAdd(a.stats + 1, (unsigned long long)((n + 7) / 8));
+            }
             cn[rw] = 0;  // before the buffer is handed back
 #pragma unroll
             for (int i = 0; i < kOwn; ++i)
@@ -505,19 +516,19 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Initial tau_g: the exact k-th best distance of each query among the first kSeedRows rows of its
+// Initial tau_g: the exact k-th best distance of each query among the first rows (128 by default) of its
 // first probed bucket (one warp per query, one or two rows per lane).  Any k candidates bound the
 // final k-th distance from above, so this is a valid threshold from the very first tile; without it
 // every (query, bucket) list starts empty and the first 128-row tile of each bucket survives the
 // filter whole.  The bound is inflated by a few ulps-of-the-sum because the re-rank sums the same
 // terms in a different order.
-constexpr int kSeedRows = 64;
+constexpr int kMaxSeedRows = 256;
 
 template <int METRIC>
 __global__ void __launch_bounds__(128)
     seed_tau_kernel(const float* __restrict__ qn, const int* __restrict__ probes,
                     const int* __restrict__ offsets, const float* __restrict__ xs, int n_buckets, int p,
-                    int d, int d_pad, int k, long long n_queries, float* __restrict__ tau_g) {
+                    int d, int d_pad, int k, int seed_rows, long long n_queries, float* __restrict__ tau_g) {
   const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= n_queries) return;
   const int lane = lane_id();
@@ -525,24 +536,39 @@ __global__ void __launch_bounds__(128)
   if (b < 0 || b >= n_buckets) return;
   const int r0 = offsets[b];
   int n = offsets[b + 1] - r0;
-  if (n > kSeedRows) n = kSeedRows;
+  if (n > seed_rows) n = seed_rows;
   if (n < k) return;
-  const float* qv = qn + q * d_pad;
-  float dist[2];
+  // 8 lanes per row, four rows per step: lane l8 reads the 16-byte chunks l8, l8 + 8, ... of its row
+  // (each group of 8 lanes reads whole 128-byte lines) against its own chunks of the query
+  const int l8 = lane & 7, g = lane >> 3;
+  const int nvec = d_pad >> 2;  // float4 chunks per row (<= 32 on this path)
+  float4 qv[4];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int r = lane + 32 * h;
+  for (int i = 0; i < 4; ++i) {
+    const int c = l8 + 8 * i;
+    qv[i] = c < nvec ? *reinterpret_cast<const float4*>(qn + q * d_pad + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  WarpTopK<1, int> top;
+  top.init(NLSH_ID_SENTINEL);
+  for (int base = 0; base < n; base += 4) {
+    const int r = base + g;
     float acc = 0.f, xx = 0.f;
     if (r < n) {
       const float* xr = xs + (size_t)(r0 + r) * d_pad;
-      for (int c = 0; c < d; c += 4) {
-        const float4 x4 = *reinterpret_cast<const float4*>(xr + c);
-        const float4 q4 = *reinterpret_cast<const float4*>(qv + c);
-        const float xa[4] = {x4.x, x4.y, x4.z, x4.w};
-        const float qa[4] = {q4.x, q4.y, q4.z, q4.w};
+      float4 xv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = l8 + 8 * i;
+        xv[i] = c < nvec ? *reinterpret_cast<const float4*>(xr + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int col0 = 4 * (l8 + 8 * i);
+        const float xa[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+        const float qa[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          if (c + e < d) {
+          if (col0 + e < d) {
             if (METRIC == NLSH_METRIC_L2) {
               const float t = (qa[e] - xa[e]) + 1e-6f;
               acc = fmaf(t, t, acc);
@@ -554,12 +580,14 @@ __global__ void __launch_bounds__(128)
         }
       }
     }
-    dist[h] = METRIC == NLSH_METRIC_L2 ? acc : 1.0f - acc / fmaxf(sqrtf(xx), 1e-8f);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      acc += __shfl_xor_sync(NLSH_FULL_MASK, acc, o);
+      if (METRIC != NLSH_METRIC_L2) xx += __shfl_xor_sync(NLSH_FULL_MASK, xx, o);
+    }
+    const float dist = METRIC == NLSH_METRIC_L2 ? acc : 1.0f - acc / fmaxf(sqrtf(xx), 1e-8f);
+    top.offer(dist, r, l8 == 0 && r < n, k);
   }
-  WarpTopK<1, int> top;
-  top.init(NLSH_ID_SENTINEL);
-  top.seed32(dist[0], lane, lane < n, NLSH_ID_SENTINEL, k);
-  top.offer(dist[1], lane + 32, lane + 32 < n, k);
   if (lane == 0 && top.tau < pos_inf()) {
     const float t = top.tau;
     tau_g[q] = METRIC == NLSH_METRIC_L2 ? t * 1.00002f + 1e-30f : t + 4e-6f + 2e-5f * fabsf(t);
@@ -595,15 +623,17 @@ int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, 
   gather_pair_queries_kernel<<<(unsigned)blocks, 256, 0, st>>>(qn, pairs, n_valid, n_pairs, p, d_pad, qs,
                                                              qs_norm, tau_g, n_queries);
   NLSH_CUDA_TRY(nlsh_post_launch());
-  const char* env = getenv("NLSH_SCAN_SEED");  // NLSH_SCAN_SEED=0: no seeding (A/B runs)
-  if (env != nullptr && env[0] == '0') return NLSH_OK;
+  int seed_rows = 128;
+  if (const char* env = getenv("NLSH_SCAN_SEED")) seed_rows = atoi(env);  // rows sampled; 0 = no seeding (A/B runs)
+  if (seed_rows <= 0) return NLSH_OK;
+  if (seed_rows > kMaxSeedRows) seed_rows = kMaxSeedRows;
   const unsigned sb = (unsigned)((n_queries + 3) / 4);
   if (metric == NLSH_METRIC_L2)
     seed_tau_kernel<NLSH_METRIC_L2><<<sb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad, k,
-                                                       n_queries, tau_g);
+                                                       seed_rows, n_queries, tau_g);
   else
     seed_tau_kernel<NLSH_METRIC_ANGULAR><<<sb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad,
-                                                            k, n_queries, tau_g);
+                                                            k, seed_rows, n_queries, tau_g);
   return nlsh_check_cuda(nlsh_post_launch(), "seed_tau_kernel launch");
 }
 

@@ -26,6 +26,7 @@ struct TcScanArgs {
   const int* n_items;    // device scalar
   int max_items;
   int* item_counter;
+  unsigned long long* stats;  // optional debug counters {survivors, re-rank batches} (or nullptr)
   float* tau_g;          // [n_queries] best known upper bound of each query's final k-th distance
   float* part_d;         // [n_queries * p, max_chunks, k]
   int* part_id;          // ROW indices into xs (merge_partials_kernel maps them through ids)

@@ -60,6 +60,7 @@ PROTOTYPES = {
     "nlsh_query_scan_topk": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64,
                                             _i64, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _u32,
                                             _vp]),
+    "nlsh_query_scan_impl": (ctypes.c_int, [_i32, _i32, _i32, _i32]),
     "nlsh_knn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "nlsh_knn_bruteforce": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _i64,
                                            _vp, _vp, _vp, _sz, _vp]),
@@ -314,6 +315,11 @@ def query_scan_topk(xq, probes, offsets, ids, x_sorted, d, max_bucket_rows, metr
                                         _ptr(ws), ws.numel(), flags, _stream())
     _check(rc, "nlsh_query_scan_topk")
     return out_ids, out_d, out_n
+
+
+def scan_impl(d, k, metric, has_sqnorm=True):
+    """Which scan kernel nlsh_query_scan_topk runs for this shape: 1 = tensor-core filtered, 0 = fp32 SIMT."""
+    return int(lib().nlsh_query_scan_impl(d, k, metric, 1 if has_sqnorm else 0))
 
 
 def knn_bruteforce(xq, xdb, metric, k, exclude_self=False, self_offset=0, id_offset=0):
