@@ -40,7 +40,7 @@
 //                  32 fp32) into the slot ring;
 //   warp 1 lane 0  MMA issuer: per tile and K block 4 x tcgen05.mma M128 N32 K8 into one of two
 //                  TMEM accumulator sets; tcgen05.commit frees the slot, the last one of a tile
-//                  signals acc_full - shared memory only ever holds tiles in flight;
+//                  signals acc_full - a slot lives from its TMA issue to the end of its MMAs;
 //   warps 2-5      filter: thread = row; tcgen05.ld its 32 scores (then the TMEM set is free
 //                  again), bound + compare, survivors appended to the list of the re-rank warp
 //                  that owns the query (warp-aggregated shared-memory atomics; 4-deep list ring);
@@ -76,6 +76,7 @@ constexpr uint32_t kQBoxBytes = kTcNQ * kTcBK * sizeof(float);   // 4 KB: one K 
 constexpr int kMaxSlots = 16;
 constexpr int kMetaFloats = kTile + 4;           // a tile's row norms, from the 16-byte boundary below its first row
 constexpr uint32_t kMetaBytes = 640;            // kMetaFloats * 4 rounded up to 128
+constexpr int kMetaBufs = 8;                    // row-norm ring depth (tiles)
 constexpr int kMaxKBlocks = 4;                  // d_pad <= 128
 constexpr float kFilterC = 0.001953125f * 1.02f + 4e-5f;  // see header comment
 constexpr float kAngularC = 2.1e-3f;
@@ -96,30 +97,38 @@ __device__ __forceinline__ float make_thr(float eff, float qn2, float l2_slack) 
   return eff - 1.0f + kAngularC;
 }
 
-// Exact distance of row r of the tile (shared memory) to query j of the item, 4 lanes per pair:
-// lane l4 owns the columns = l4 (mod 4) and walks them in ascending order, the columns of a
-// partial last float4 (d % 4 != 0) go to lane 0, and the four partial sums are combined as
-// (s0 + s1) + (s2 + s3).  That is exactly the summation order of scan.cu::consume_box (packed
-// float2 accumulators over the columns 0,1 / 2,3 of each float4), so both scan kernels produce
-// the same bits for the same (q, x) - the parity tests compare them with torch.equal.  Both
-// operands sit in SWIZZLE_128B boxes: 16-byte chunk c of row r is stored at chunk position
-// c ^ (r & 7).  L2 returns the squared distance (the root is taken in merge_partials_kernel).
+// Exact distance of database row `xrow` (global memory; an L2 hit, the tile has just streamed
+// through) to query j of the item (shared memory, SWIZZLE_128B box: 16-byte chunk c of row j is
+// stored at chunk position c ^ (j & 7)), 4 lanes per pair: lane l4 owns the columns = l4 (mod 4)
+// and walks them in ascending order, the columns of a partial last float4 (d % 4 != 0) go to
+// lane 0, and the four partial sums are combined as (s0 + s1) + (s2 + s3).  That is exactly the
+// summation order of scan.cu::consume_box (packed float2 accumulators over the columns 0,1 / 2,3
+// of each float4), so both scan kernels produce the same bits for the same (q, x) - the parity
+// tests compare them with torch.equal.  All loads of the row are issued before the dependent sum.
+// L2 returns the squared distance (the root is taken in merge_partials_kernel).
 template <int METRIC>
-__device__ __noinline__ float exact_distance(const unsigned char* slots, unsigned ring, unsigned n_slots,
-                                             const unsigned char* qsrc, int d, int r, int j, int l4) {
+__device__ __noinline__ float exact_distance(const float* __restrict__ xrow, const unsigned char* qsrc,
+                                             int d, int j, int l4) {
   float acc = 0.f, xx = 0.f;
   const int nv = d >> 2, tail = d & 3;
-  const int xrow = r * 128 + l4 * 4, xsw = r & 7;
   const int qrow = j * 128 + l4 * 4, qsw = j & 7;
+  float xv[kMaxKBlocks * 8];
+#pragma unroll
+  for (int v = 0; v < kMaxKBlocks * 8; ++v) xv[v] = v < nv ? __ldg(xrow + 4 * v + l4) : 0.f;
+  float xt[3] = {0.f, 0.f, 0.f};
+  if (tail != 0 && l4 == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c < tail) xt[c] = __ldg(xrow + nv * 4 + c);
+  }
 #pragma unroll
   for (int kb = 0; kb < kMaxKBlocks; ++kb) {
     if (kb * 8 < nv) {
-      const unsigned char* xs = slots + (size_t)((ring + (unsigned)kb) % n_slots) * kSlotBytes + xrow;
       const unsigned char* qs = qsrc + kb * kQBoxBytes + qrow;
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {
         if (kb * 8 + c8 < nv) {
-          const float x = *reinterpret_cast<const float*>(xs + ((c8 ^ xsw) << 4));
+          const float x = xv[kb * 8 + c8];
           const float q = *reinterpret_cast<const float*>(qs + ((c8 ^ qsw) << 4));
           if (METRIC == NLSH_METRIC_L2) {
             // F.pairwise_distance: (q - x) + eps, squared and summed (nlsh/data.py:201)
@@ -135,16 +144,17 @@ __device__ __noinline__ float exact_distance(const unsigned char* slots, unsigne
   }
   if (tail != 0 && l4 == 0) {  // the partial float4 at vector index nv: columns 4 nv .. d - 1
     const int kb = nv >> 3, c8 = nv & 7;
-    const float* xs = reinterpret_cast<const float*>(
-        slots + (size_t)((ring + (unsigned)kb) % n_slots) * kSlotBytes + r * 128 + ((c8 ^ xsw) << 4));
     const float* qs = reinterpret_cast<const float*>(qsrc + kb * kQBoxBytes + j * 128 + ((c8 ^ qsw) << 4));
-    for (int c = 0; c < tail; ++c) {
-      if (METRIC == NLSH_METRIC_L2) {
-        const float t = __fadd_rn(__fsub_rn(qs[c], xs[c]), 1e-6f);
-        acc = fmaf(t, t, acc);
-      } else {
-        acc = fmaf(qs[c], xs[c], acc);
-        xx = fmaf(xs[c], xs[c], xx);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c < tail) {
+        if (METRIC == NLSH_METRIC_L2) {
+          const float t = __fadd_rn(__fsub_rn(qs[c], xt[c]), 1e-6f);
+          acc = fmaf(t, t, acc);
+        } else {
+          acc = fmaf(qs[c], xt[c], acc);
+          xx = fmaf(xt[c], xt[c], xx);
+        }
       }
     }
   }
@@ -164,8 +174,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   unsigned char* base = stc_smem_raw + ((1024u - (smem_u32(stc_smem_raw) & 1023u)) & 1023u);
   unsigned char* slots = base;                                              // [n_slots][16 KB]
   unsigned char* qbuf = slots + (size_t)a.n_slots * kSlotBytes;             // [2][kblocks][4 KB]
-  unsigned char* meta = qbuf + (size_t)2 * a.kblocks * kQBoxBytes;          // [n_slots][kMetaBytes] row norms
-  uint16_t* surv = reinterpret_cast<uint16_t*>(meta + (size_t)a.n_slots * kMetaBytes);  // [kSurvBufs][kRerankWarps][kListCap]
+  unsigned char* meta = qbuf + (size_t)2 * a.kblocks * kQBoxBytes;          // [kMetaBufs][kMetaBytes] row norms
+  uint16_t* surv = reinterpret_cast<uint16_t*>(meta + (size_t)kMetaBufs * kMetaBytes);  // [kSurvBufs][kRerankWarps][kListCap]
   float* thr_s = reinterpret_cast<float*>(surv + kSurvBufs * kRerankWarps * kListCap);      // [2][kTcNQ]
   float* own_ext = thr_s + 2 * kTcNQ;                                       // [2][kTcNQ]
   float* own_qn2 = own_ext + 2 * kTcNQ;                                     // [2][kTcNQ]
@@ -180,7 +190,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* acc_empty = acc_full + 2;                                       // [2]
   uint64_t* surv_full = acc_empty + 2;                                      // [kSurvBufs]
   uint64_t* surv_empty = surv_full + kSurvBufs;                             // [kSurvBufs]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(surv_empty + kSurvBufs);
+  uint64_t* meta_full = surv_empty + kSurvBufs;                             // [kMetaBufs]
+  uint64_t* meta_empty = meta_full + kMetaBufs;                             // [kMetaBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta_empty + kMetaBufs);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -191,7 +203,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (tid == 0) {
     for (int s = 0; s < a.n_slots; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kRerankWarps);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kMetaBufs; ++s) {
+      mbar_init(&meta_full[s], 1);
+      mbar_init(&meta_empty[s], kFilterWarps);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
@@ -216,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // =================================== producer =========================================
     int total = *a.n_items;
     if (total > a.max_items) total = a.max_items;
-    unsigned ring = 0, icount = 0;
+    unsigned ring = 0, icount = 0, tcount = 0;
     while (true) {
       int item = 0;
       if (lane == 0) item = atomicAdd(a.item_counter, 1);
@@ -253,27 +269,30 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int kb = 0; kb < kblocks; ++kb)
           tma_load_2d(qdst + kb * kQBoxBytes, &map_q, kb * kTcBK, rec.pair_base, &q_full[islot]);
         const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
-        for (int t = 0; t < n_tiles; ++t) {
+        for (int t = 0; t < n_tiles; ++t, ++tcount) {
           const int trow0 = rec.row0 + t * kTile;
+          {
+            // The tile's row norms: a plain bulk copy needs a 16-byte aligned source, so it starts
+            // at the 4-row boundary below the tile and stops at the last whole group of 4 rows of
+            // the array (the filter reads the <= 3 rows after that directly).
+            const unsigned mb = tcount % kMetaBufs;
+            MBAR_WAIT(&meta_empty[mb], ((tcount / kMetaBufs) & 1u) ^ 1u);
+            const long long m0 = trow0 & ~3ll;
+            long long avail = (a.n_rows & ~3ll) - m0;
+            if (avail > kMetaFloats) avail = kMetaFloats;
+            if (avail > 0) {
+              mbar_arrive_expect_tx(&meta_full[mb], (unsigned)avail * 4u);
+              bulk_g2s(meta + (size_t)mb * kMetaBytes, a.xnorm + m0, (unsigned)avail * 4u, &meta_full[mb]);
+            } else {
+              mbar_arrive(&meta_full[mb]);
+            }
+          }
           for (int kb = 0; kb < kblocks; ++kb, ++ring) {
             const unsigned s = ring % n_slots;
             MBAR_WAIT(&empty_bar[s], ((ring / n_slots) & 1u) ^ 1u);
-            // a box is always written in full (rows / columns past the tensor are zero filled);
-            // the tile's row norms and row ids ride on its first slot
-            // a box is always written in full (rows / columns past the tensor are zero filled).
-            // The tile's row norms ride on its first slot: a plain bulk copy needs a 16-byte aligned
-            // source, so it starts at the 4-row boundary below the tile and stops at the last whole
-            // group of 4 rows of the array (the filter reads the <= 3 rows after that directly).
-            unsigned extra = 0;
-            const long long m0 = trow0 & ~3ll;
-            if (kb == 0) {
-              long long avail = (a.n_rows & ~3ll) - m0;
-              if (avail > kMetaFloats) avail = kMetaFloats;
-              if (avail > 0) extra = (unsigned)avail * 4u;
-            }
-            mbar_arrive_expect_tx(&full_bar[s], kSlotBytes + extra);
+            // a box is always written in full (rows / columns past the tensor are zero filled)
+            mbar_arrive_expect_tx(&full_bar[s], kSlotBytes);
             tma_load_2d(slots + (size_t)s * kSlotBytes, &map_x, kb * kTcBK, trow0, &full_bar[s]);
-            if (extra) bulk_g2s(meta + (size_t)s * kMetaBytes, a.xnorm + m0, extra, &full_bar[s]);
           }
         }
       }
@@ -307,8 +326,9 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int k8 = 0; k8 < kTcBK / 8; ++k8)  // UMMA K = 8 tf32 = 32 bytes: +2 in (addr >> 4)
               tc_mma_tf32(acc, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc,
                           (kb > 0 || k8 > 0) ? 1u : 0u);
+            tc_commit(&empty_bar[s]);  // the slot may be refilled once these MMAs have read it
           }
-          tc_commit(&acc_full[set]);  // the slots are released by the re-rank warps, not here
+          tc_commit(&acc_full[set]);
         }
         ++icount;
       }
@@ -319,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int quarter = warp & 3;  // TMEM lanes this warp may read
     const int r_local = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    unsigned ring = 0, icount = 0, tcount = 0;
+    unsigned icount = 0, tcount = 0;
     while (true) {
       const int islot = (int)(icount & 1u);
       MBAR_WAIT(&q_full[islot], (icount >> 1) & 1u);
@@ -330,11 +350,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int t = 0; t < n_tiles; ++t, ++tcount) {
         const int row = rec.row0 + t * kTile + r_local;
         const bool valid = row < rec.row1;
-        const unsigned s0 = ring % n_slots;  // the tile's first slot carries its row norms
-        MBAR_WAIT(&full_bar[s0], (ring / n_slots) & 1u);
-        float xn = reinterpret_cast<const float*>(meta + (size_t)s0 * kMetaBytes)[((rec.row0 + t * kTile) & 3) + r_local];
+        const unsigned mb = tcount % kMetaBufs;
+        MBAR_WAIT(&meta_full[mb], (tcount / kMetaBufs) & 1u);
+        float xn = reinterpret_cast<const float*>(meta + (size_t)mb * kMetaBytes)[((rec.row0 + t * kTile) & 3) + r_local];
         if (row >= (a.n_rows & ~3ll)) xn = valid ? a.xnorm[row] : 0.f;
-        ring += (unsigned)kblocks;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&meta_empty[mb]);
         const unsigned set = tcount & 1u;
         MBAR_WAIT(&acc_full[set], (tcount >> 1) & 1u);
         tc_fence_after();
@@ -394,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // =================================== re-rank ===========================================
     const int rw = warp - 2 - kFilterWarps;  // owner index: lists of queries j = rw + kRerankWarps * i
     const int l4 = lane & 3;
-    unsigned ring = 0, icount = 0, tcount = 0;
+    unsigned icount = 0, tcount = 0;
     while (true) {
       const int islot = (int)(icount & 1u);
       MBAR_WAIT(&q_full[islot], (icount >> 1) & 1u);
@@ -422,10 +443,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         int* cn = cnt + sb * kRerankWarps;
         const int n = cn[rw];
         if (n > 0) {  // warp-uniform
-          for (int kb = 0; kb < kblocks; ++kb) {
-            const unsigned rr = ring + (unsigned)kb;  // completed long ago: the wait makes the TMA
-            MBAR_WAIT(&full_bar[rr % n_slots], (rr / n_slots) & 1u);  // writes visible to this thread
-          }
           const uint16_t* mine_sv = surv + ((size_t)sb * kRerankWarps + rw) * kListCap;
           const int trow0 = rec.row0 + t * kTile;
           for (int b0 = 0; b0 < n; b0 += 8) {
@@ -436,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             // lists carry the ROW index: inside a bucket rows ascend with the ids (nlsh_build_csr), so
             // (distance, row) orders like (distance, id); merge_partials_kernel maps rows to ids
             const int cand = trow0 + r;
-            const float dist = exact_distance<METRIC>(slots, ring, n_slots, qsrc, a.d, r, j, l4);
+            const float dist = exact_distance<METRIC>(a.xs + (size_t)cand * a.d_pad, qsrc, a.d, j, l4);
             const int own = j >> kRerankShift;  // j = rw + kRerankWarps * own
 #pragma unroll
             for (int i = 0; i < kOwn; ++i)
@@ -454,11 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&surv_empty[sb]);
-          for (int kb = 0; kb < kblocks; ++kb) mbar_arrive(&empty_bar[(ring + (unsigned)kb) % n_slots]);
-        }
-        ring += (unsigned)kblocks;
+        if (lane == 0) mbar_arrive(&surv_empty[sb]);
       }
 
       // ------------------------------- item done: partial lists ------------------------------
@@ -595,10 +608,10 @@ __global__ void __launch_bounds__(128)
 }
 
 size_t scan_tc_smem(int kblocks, int n_slots) {
-  return (size_t)n_slots * (kSlotBytes + kMetaBytes) + (size_t)2 * kblocks * kQBoxBytes +
+  return (size_t)n_slots * kSlotBytes + (size_t)kMetaBufs * kMetaBytes + (size_t)2 * kblocks * kQBoxBytes +
          kSurvBufs * kRerankWarps * kListCap * sizeof(uint16_t) + 8 * kTcNQ * sizeof(float) +
          kSurvBufs * kRerankWarps * sizeof(int) + 2 * sizeof(TcItem) +
-         (2 * kMaxSlots + 8 + 2 * kSurvBufs) * sizeof(uint64_t) + 16 + 1024;
+         (2 * kMaxSlots + 8 + 2 * kSurvBufs + 2 * kMetaBufs) * sizeof(uint64_t) + 16 + 1024;
 }
 
 }  // namespace
