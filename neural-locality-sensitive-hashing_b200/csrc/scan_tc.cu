@@ -36,7 +36,7 @@
 //   warp 0         producer: owns the work queue (atomic counter).  Per item the 32 lanes fetch the
 //                  per-query state (flat probe index, |q|^2, tau_g -> initial thresholds) into
 //                  shared memory, lane 0 TMA-loads the item's queries (box 32 rows x 32 fp32 per K
-//                  block, SWIZZLE_128B; 2-deep item ring) and streams the row tiles (box 128 rows x
+//                  block, SWIZZLE_128B; 4-deep item ring) and streams the row tiles (box 128 rows x
 //                  32 fp32) into the slot ring;
 //   warp 1 lane 0  MMA issuer: per tile and K block 4 x tcgen05.mma M128 N32 K8 into one of two
 //                  TMEM accumulator sets; tcgen05.commit frees the slot, the last one of a tile
@@ -63,6 +63,18 @@ namespace {
 #define MBAR_WAIT mbar_wait_poll
 #endif
 
+// Debug timing (NLSH_TC_STATS): cycles block 0 spends in each wait, summed into a.stats[slot].
+#define TIMED_WAIT(slot, bar, par)                                  \
+  do {                                                             \
+    if (timing) {                                                  \
+      const long long t0_ = clock64();                             \
+      MBAR_WAIT(bar, par);                                         \
+      tacc[slot] += clock64() - t0_;                               \
+    } else {                                                       \
+      MBAR_WAIT(bar, par);                                         \
+    }                                                              \
+  } while (0)
+
 constexpr int kFilterWarps = 4;                 // one per TMEM lane quarter
 constexpr int kRerankWarps = 8;                 // two per scheduler: their latencies overlap
 constexpr int kRerankShift = 3;                 // log2(kRerankWarps)
@@ -77,6 +89,8 @@ constexpr int kMaxSlots = 16;
 constexpr int kMetaFloats = kTile + 4;           // a tile's row norms, from the 16-byte boundary below its first row
 constexpr uint32_t kMetaBytes = 640;            // kMetaFloats * 4 rounded up to 128
 constexpr int kMetaBufs = 8;                    // row-norm ring depth (tiles)
+constexpr int kItemBufs = 4;                    // item ring depth: buckets of a few tiles are shorter than the
+                                                // pipeline, so several items must be in flight
 constexpr int kMaxKBlocks = 4;                  // d_pad <= 128
 constexpr float kFilterC = 0.001953125f * 1.02f + 4e-5f;  // see header comment
 constexpr float kAngularC = 2.1e-3f;
@@ -173,20 +187,20 @@ __global__ void __launch_bounds__(kThreads, 1)
   extern __shared__ unsigned char stc_smem_raw[];
   unsigned char* base = stc_smem_raw + ((1024u - (smem_u32(stc_smem_raw) & 1023u)) & 1023u);
   unsigned char* slots = base;                                              // [n_slots][16 KB]
-  unsigned char* qbuf = slots + (size_t)a.n_slots * kSlotBytes;             // [2][kblocks][4 KB]
-  unsigned char* meta = qbuf + (size_t)2 * a.kblocks * kQBoxBytes;          // [kMetaBufs][kMetaBytes] row norms
+  unsigned char* qbuf = slots + (size_t)a.n_slots * kSlotBytes;             // [kItemBufs][kblocks][4 KB]
+  unsigned char* meta = qbuf + (size_t)kItemBufs * a.kblocks * kQBoxBytes;          // [kMetaBufs][kMetaBytes] row norms
   uint16_t* surv = reinterpret_cast<uint16_t*>(meta + (size_t)kMetaBufs * kMetaBytes);  // [kSurvBufs][kRerankWarps][kListCap]
-  float* thr_s = reinterpret_cast<float*>(surv + kSurvBufs * kRerankWarps * kListCap);      // [2][kTcNQ]
-  float* own_ext = thr_s + 2 * kTcNQ;                                       // [2][kTcNQ]
-  float* own_qn2 = own_ext + 2 * kTcNQ;                                     // [2][kTcNQ]
-  int* own_f = reinterpret_cast<int*>(own_qn2 + 2 * kTcNQ);                 // [2][kTcNQ]
-  int* cnt = own_f + 2 * kTcNQ;                                             // [kSurvBufs][kRerankWarps]
-  TcItem* itm = reinterpret_cast<TcItem*>(cnt + kSurvBufs * kRerankWarps);  // [2]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(itm + 2);                // [kMaxSlots]
+  float* thr_s = reinterpret_cast<float*>(surv + kSurvBufs * kRerankWarps * kListCap);      // [kItemBufs][kTcNQ]
+  float* own_ext = thr_s + kItemBufs * kTcNQ;                               // [kItemBufs][kTcNQ]
+  float* own_qn2 = own_ext + kItemBufs * kTcNQ;                             // [kItemBufs][kTcNQ]
+  int* own_f = reinterpret_cast<int*>(own_qn2 + kItemBufs * kTcNQ);         // [kItemBufs][kTcNQ]
+  int* cnt = own_f + kItemBufs * kTcNQ;                                             // [kSurvBufs][kRerankWarps]
+  TcItem* itm = reinterpret_cast<TcItem*>(cnt + kSurvBufs * kRerankWarps);  // [kItemBufs]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(itm + kItemBufs);                // [kMaxSlots]
   uint64_t* empty_bar = full_bar + kMaxSlots;                               // [kMaxSlots]
-  uint64_t* q_full = empty_bar + kMaxSlots;                                 // [2]
-  uint64_t* q_empty = q_full + 2;                                           // [2]
-  uint64_t* acc_full = q_empty + 2;                                         // [2]
+  uint64_t* q_full = empty_bar + kMaxSlots;                                 // [kItemBufs]
+  uint64_t* q_empty = q_full + kItemBufs;                                   // [kItemBufs]
+  uint64_t* acc_full = q_empty + kItemBufs;                                 // [2]
   uint64_t* acc_empty = acc_full + 2;                                       // [2]
   uint64_t* surv_full = acc_empty + 2;                                      // [kSurvBufs]
   uint64_t* surv_empty = surv_full + kSurvBufs;                             // [kSurvBufs]
@@ -209,9 +223,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&meta_full[s], 1);
       mbar_init(&meta_empty[s], kFilterWarps);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kItemBufs; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], kRerankWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], kFilterWarps);
     }
@@ -227,6 +243,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool timing = a.stats != nullptr && blockIdx.x == 0 && lane == 0;
+  long long tacc[4] = {0, 0, 0, 0};
+  const long long t_begin = clock64();
 
   if (warp == 0) {
     // =================================== producer =========================================
@@ -237,8 +256,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       int item = 0;
       if (lane == 0) item = atomicAdd(a.item_counter, 1);
       item = __shfl_sync(NLSH_FULL_MASK, item, 0);
-      const int islot = (int)(icount & 1u);
-      MBAR_WAIT(&q_empty[islot], ((icount >> 1) & 1u) ^ 1u);
+      const int islot = (int)(icount % kItemBufs);
+      TIMED_WAIT(2, &q_empty[islot], ((icount / kItemBufs) & 1u) ^ 1u);
       if (item >= total) {
         if (lane == 0) {
           itm[islot].nq = 0;  // end of work
@@ -276,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             // at the 4-row boundary below the tile and stops at the last whole group of 4 rows of
             // the array (the filter reads the <= 3 rows after that directly).
             const unsigned mb = tcount % kMetaBufs;
-            MBAR_WAIT(&meta_empty[mb], ((tcount / kMetaBufs) & 1u) ^ 1u);
+            TIMED_WAIT(0, &meta_empty[mb], ((tcount / kMetaBufs) & 1u) ^ 1u);
             const long long m0 = trow0 & ~3ll;
             long long avail = (a.n_rows & ~3ll) - m0;
             if (avail > kMetaFloats) avail = kMetaFloats;
@@ -289,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           for (int kb = 0; kb < kblocks; ++kb, ++ring) {
             const unsigned s = ring % n_slots;
-            MBAR_WAIT(&empty_bar[s], ((ring / n_slots) & 1u) ^ 1u);
+            TIMED_WAIT(1, &empty_bar[s], ((ring / n_slots) & 1u) ^ 1u);
             // a box is always written in full (rows / columns past the tensor are zero filled)
             mbar_arrive_expect_tx(&full_bar[s], kSlotBytes);
             tma_load_2d(slots + (size_t)s * kSlotBytes, &map_x, kb * kTcBK, trow0, &full_bar[s]);
@@ -305,20 +324,20 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t idesc = make_tf32_idesc(kTcNQ);
       unsigned ring = 0, icount = 0, tcount = 0;
       while (true) {
-        const int islot = (int)(icount & 1u);
-        MBAR_WAIT(&q_full[islot], (icount >> 1) & 1u);
+        const int islot = (int)(icount % kItemBufs);
+        MBAR_WAIT(&q_full[islot], (icount / kItemBufs) & 1u);
         const int nq = itm[islot].nq;
         if (nq == 0) break;
         const int n_tiles = (itm[islot].row1 - itm[islot].row0 + kTile - 1) / kTile;
         const unsigned char* qsrc = qbuf + (size_t)islot * kblocks * kQBoxBytes;
         for (int t = 0; t < n_tiles; ++t, ++tcount) {
           const unsigned set = tcount & 1u;
-          MBAR_WAIT(&acc_empty[set], ((tcount >> 1) & 1u) ^ 1u);  // the filter drained this set
+          TIMED_WAIT(0, &acc_empty[set], ((tcount >> 1) & 1u) ^ 1u);  // the filter drained this set
           tc_fence_after();
           const uint32_t acc = tmem_base + set * (uint32_t)kTcNQ;
           for (int kb = 0; kb < kblocks; ++kb, ++ring) {
             const unsigned s = ring % n_slots;
-            MBAR_WAIT(&full_bar[s], (ring / n_slots) & 1u);
+            TIMED_WAIT(1, &full_bar[s], (ring / n_slots) & 1u);
             tc_fence_after();
             const uint64_t da = make_kmajor_sw128_desc(slots + (size_t)s * kSlotBytes);
             const uint64_t db = make_kmajor_sw128_desc(qsrc + kb * kQBoxBytes);
@@ -341,8 +360,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     unsigned icount = 0, tcount = 0;
     while (true) {
-      const int islot = (int)(icount & 1u);
-      MBAR_WAIT(&q_full[islot], (icount >> 1) & 1u);
+      const int islot = (int)(icount % kItemBufs);
+      MBAR_WAIT(&q_full[islot], (icount / kItemBufs) & 1u);
       const TcItem rec = itm[islot];
       if (rec.nq == 0) break;
       const float* th = thr_s + islot * kTcNQ;
@@ -351,13 +370,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int row = rec.row0 + t * kTile + r_local;
         const bool valid = row < rec.row1;
         const unsigned mb = tcount % kMetaBufs;
-        MBAR_WAIT(&meta_full[mb], (tcount / kMetaBufs) & 1u);
+        TIMED_WAIT(0, &meta_full[mb], (tcount / kMetaBufs) & 1u);
         float xn = reinterpret_cast<const float*>(meta + (size_t)mb * kMetaBytes)[((rec.row0 + t * kTile) & 3) + r_local];
         if (row >= (a.n_rows & ~3ll)) xn = valid ? a.xnorm[row] : 0.f;
         __syncwarp();
         if (lane == 0) mbar_arrive(&meta_empty[mb]);
         const unsigned set = tcount & 1u;
-        MBAR_WAIT(&acc_full[set], (tcount >> 1) & 1u);
+        TIMED_WAIT(1, &acc_full[set], (tcount >> 1) & 1u);
         tc_fence_after();
         uint32_t v0[16], v1[16];
         tc_ld16_nowait(lane_base + set * (uint32_t)kTcNQ, v0);
@@ -390,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         if (!valid) mask = 0;
         const unsigned sb = tcount % kSurvBufs, use = tcount / kSurvBufs;
-        MBAR_WAIT(&surv_empty[sb], (use & 1u) ^ 1u);  // the re-rank warps are done with this buffer
+        TIMED_WAIT(2, &surv_empty[sb], (use & 1u) ^ 1u);  // the re-rank warps are done with this buffer
         int* cn = cnt + sb * kRerankWarps;
         uint16_t* sv = surv + (size_t)sb * kRerankWarps * kListCap;
         unsigned any = __reduce_or_sync(NLSH_FULL_MASK, mask);
@@ -417,20 +436,21 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int l4 = lane & 3;
     unsigned icount = 0, tcount = 0;
     while (true) {
-      const int islot = (int)(icount & 1u);
-      MBAR_WAIT(&q_full[islot], (icount >> 1) & 1u);
+      const int islot = (int)(icount % kItemBufs);
+      MBAR_WAIT(&q_full[islot], (icount / kItemBufs) & 1u);
       const TcItem rec = itm[islot];
       if (rec.nq == 0) break;
       const unsigned char* qsrc = qbuf + (size_t)islot * kblocks * kQBoxBytes;
       float* th = thr_s + islot * kTcNQ;
 
       WarpTopK<1, int> top[kOwn];
-      float ext[kOwn], qn2[kOwn];
+      float ext[kOwn], qn2[kOwn], tau_seen[kOwn];
       int fidx[kOwn];
 #pragma unroll
       for (int i = 0; i < kOwn; ++i) {
         const int j = rw + kRerankWarps * i;
         top[i].init(NLSH_ID_SENTINEL);
+        tau_seen[i] = pos_inf();
         fidx[i] = own_f[islot * kTcNQ + j];
         ext[i] = own_ext[islot * kTcNQ + j];
         qn2[i] = own_qn2[islot * kTcNQ + j];
@@ -439,9 +459,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
       for (int t = 0; t < n_tiles; ++t, ++tcount) {
         const unsigned sb = tcount % kSurvBufs, use = tcount / kSurvBufs;
-        MBAR_WAIT(&surv_full[sb], use & 1u);
+        TIMED_WAIT(0, &surv_full[sb], use & 1u);
         int* cn = cnt + sb * kRerankWarps;
         const int n = cn[rw];
+        const long long tb0 = timing ? clock64() : 0;
         if (n > 0) {  // warp-uniform
           const uint16_t* mine_sv = surv + ((size_t)sb * kRerankWarps + rw) * kListCap;
           const int trow0 = rec.row0 + t * kTile;
@@ -453,11 +474,19 @@ __global__ void __launch_bounds__(kThreads, 1)
             // lists carry the ROW index: inside a bucket rows ascend with the ids (nlsh_build_csr), so
             // (distance, row) orders like (distance, id); merge_partials_kernel maps rows to ids
             const int cand = trow0 + r;
+            const long long td0 = timing ? clock64() : 0;
             const float dist = exact_distance<METRIC>(a.xs + (size_t)cand * a.d_pad, qsrc, a.d, j, l4);
+            if (timing) tacc[2] += clock64() - td0;
             const int own = j >> kRerankShift;  // j = rw + kRerankWarps * own
+            bool pass = false;
 #pragma unroll
             for (int i = 0; i < kOwn; ++i)
-              top[i].offer(dist, cand, has && l4 == 0 && own == i && dist <= ext[i], a.k);
+              pass |= own == i && dist <= ext[i] && lex_less<int>(dist, cand, top[i].tau, top[i].tau_id);
+            pass &= has && l4 == 0;
+            if (__any_sync(NLSH_FULL_MASK, pass)) {
+#pragma unroll
+              for (int i = 0; i < kOwn; ++i) top[i].offer(dist, cand, pass && own == i, a.k);
+            }
           }
           if (lane == 0) {
             if (a.stats != nullptr) {  // debug counters: survivors, batches
@@ -466,10 +495,15 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             cn[rw] = 0;  // before the buffer is handed back
 #pragma unroll
-            for (int i = 0; i < kOwn; ++i)
-              th[rw + kRerankWarps * i] = make_thr<METRIC>(fminf(top[i].tau, ext[i]), qn2[i], a.l2_slack);
+            for (int i = 0; i < kOwn; ++i) {
+              if (top[i].tau < tau_seen[i]) {  // only a list that tightened moves its threshold
+                tau_seen[i] = top[i].tau;
+                th[rw + kRerankWarps * i] = make_thr<METRIC>(fminf(top[i].tau, ext[i]), qn2[i], a.l2_slack);
+              }
+            }
           }
         }
+        if (timing && n > 0) tacc[1] += clock64() - tb0;
         __syncwarp();
         if (lane == 0) mbar_arrive(&surv_empty[sb]);
       }
@@ -494,6 +528,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   }
 
+  if (timing && (warp == 0 || warp == 1 || warp == 2 || warp == 2 + kFilterWarps)) {
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : (warp == 2 ? 2 : 3));
+    tacc[3] = clock64() - t_begin;
+    for (int i = 0; i < 4; ++i) atomicAdd(a.stats + 2 + role * 4 + i, (unsigned long long)tacc[i]);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tc_dealloc(tmem_base, 64);
@@ -608,10 +647,10 @@ __global__ void __launch_bounds__(128)
 }
 
 size_t scan_tc_smem(int kblocks, int n_slots) {
-  return (size_t)n_slots * kSlotBytes + (size_t)kMetaBufs * kMetaBytes + (size_t)2 * kblocks * kQBoxBytes +
-         kSurvBufs * kRerankWarps * kListCap * sizeof(uint16_t) + 8 * kTcNQ * sizeof(float) +
-         kSurvBufs * kRerankWarps * sizeof(int) + 2 * sizeof(TcItem) +
-         (2 * kMaxSlots + 8 + 2 * kSurvBufs + 2 * kMetaBufs) * sizeof(uint64_t) + 16 + 1024;
+  return (size_t)n_slots * kSlotBytes + (size_t)kMetaBufs * kMetaBytes + (size_t)kItemBufs * kblocks * kQBoxBytes +
+         kSurvBufs * kRerankWarps * kListCap * sizeof(uint16_t) + 4 * kItemBufs * kTcNQ * sizeof(float) +
+         kSurvBufs * kRerankWarps * sizeof(int) + kItemBufs * sizeof(TcItem) +
+         (2 * kMaxSlots + 4 + 2 * kItemBufs + 2 * kSurvBufs + 2 * kMetaBufs) * sizeof(uint64_t) + 16 + 1024;
 }
 
 }  // namespace
@@ -654,8 +693,8 @@ int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {
   a.kblocks = (a.d_pad + kTcBK - 1) / kTcBK;
   a.l2_slack = 2.1e-6f * sqrtf((float)a.d);
   int n_slots = kMaxSlots;
-  while (n_slots > 2 * a.kblocks && scan_tc_smem(a.kblocks, n_slots) > 224 * 1024) --n_slots;
-  if (n_slots < 2 * a.kblocks) n_slots = 2 * a.kblocks;
+  // each K block's slot is freed by its own tcgen05.commit, so any ring depth >= 2 makes progress
+  while (n_slots > 3 && scan_tc_smem(a.kblocks, n_slots) > 224 * 1024) --n_slots;
   a.n_slots = n_slots;
   const size_t smem = scan_tc_smem(a.kblocks, n_slots);
   CUtensorMap map_x, map_q;

@@ -12,11 +12,17 @@ dev = torch.device("cuda")
 X = synth.make_database(n, d, hs, seed, dev, sep=bench.SEP); Q = synth.make_queries(nq, d, hs, seed, dev, sep=bench.SEP)
 hashing, _ = bench.make_hashing(d, hs, metric, seed, dev, 300)
 idx = Indexer(hashing, X, hashing.distance, metric=metric)
-for rows in (0, 64, 128, 256):
+for rows in (128, 256):
     os.environ["NLSH_SCAN_SEED"] = str(rows)
     ids, dd, nc = idx.query_tensors(Q, k=k, hash_times=p); torch.cuda.synchronize()
     ws = list(_native._workspaces.values())[0]
     B = 1 << hs
-    st = ws.view(torch.uint8)[(2 * B + 2) * 4:(2 * B + 2) * 4 + 16].view(torch.int64).cpu().tolist()
+    st = ws.view(torch.uint8)[(2 * B + 2) * 4:(2 * B + 2) * 4 + 18 * 8].view(torch.int64).cpu().tolist()
     pairs = int(nc.long().sum())
+    names = ["producer: wait meta_empty, wait slot empty, wait q_empty, total",
+             "mma: wait acc_empty, wait slot full, -, total",
+             "filter: wait meta_full, wait acc_full, wait surv_empty, total",
+             "rerank: wait surv_full, batch cycles, batches, total"]
+    for r in range(4):
+        print("   ", names[r], st[2 + 4 * r: 6 + 4 * r])
     print(f"seed_rows={rows}: candidates(pairs)={pairs} survivors={st[0]} ({st[0]/pairs*100:.2f}%) batches={st[1]} per query={st[0]/nq:.0f}")

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 ( timeout 600 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
-for f in tests/test_gpu_hash.py tests/test_gpu_build.py tests/test_gpu_query.py tests/test_gpu_knn.py tests/test_gpu_api.py; do
+for f in tests/test_gpu_hash.py tests/test_gpu_tc.py tests/test_gpu_build.py tests/test_gpu_query.py tests/test_gpu_knn.py tests/test_gpu_api.py; do
   name=$(basename $f .py)
   ( timeout 900 python -m pytest $f -m gpu -q -x --timeout=600 -s ) > gpurun_out/$name.log 2>&1
   echo "exit $?" >> gpurun_out/$name.log
