@@ -663,7 +663,7 @@ bool nlsh_scan_tc_supported(int d, int k, int metric) {
 int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, long long n_pairs,
                          int p, int d_pad, float* qs, float* qs_norm, float* tau_g,
                          long long n_queries, const int* probes, const int* offsets, const float* xs,
-                         int n_buckets, int d, int k, int metric, cudaStream_t st) {
+                         long long n_rows, int n_buckets, int d, int k, int metric, cudaStream_t st) {
   long long threads = n_pairs * 32;
   if (threads < n_queries) threads = n_queries;
   long long blocks = (threads + 255) / 256;
@@ -675,8 +675,13 @@ int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, 
   gather_pair_queries_kernel<<<(unsigned)blocks, 256, 0, st>>>(qn, pairs, n_valid, n_pairs, p, d_pad, qs,
                                                              qs_norm, tau_g, n_queries);
   NLSH_CUDA_TRY(nlsh_post_launch());
-  int seed_rows = 128;
-  if (const char* env = getenv("NLSH_SCAN_SEED")) seed_rows = atoi(env);  // rows sampled; 0 = no seeding (A/B runs)
+  // rows sampled per bucket: a quarter of the average bucket, between 32 and 128
+  // (NLSH_SCAN_SEED=<rows> overrides; 0 = no seeding, for A/B runs)
+  const long long avg = n_buckets > 0 ? n_rows / n_buckets : 0;
+  int seed_rows = (int)(avg / 4 / 32 * 32);
+  if (seed_rows < 32) seed_rows = 32;
+  if (seed_rows > 128) seed_rows = 128;
+  if (const char* env = getenv("NLSH_SCAN_SEED")) seed_rows = atoi(env);
   if (seed_rows <= 0) return NLSH_OK;
   if (seed_rows > kMaxSeedRows) seed_rows = kMaxSeedRows;
   const unsigned sb = (unsigned)((n_queries + 3) / 4);

@@ -42,5 +42,5 @@ bool nlsh_scan_tc_supported(int d, int k, int metric);
 int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, long long n_pairs,
                          int p, int d_pad, float* qs, float* qs_norm, float* tau_g,
                          long long n_queries, const int* probes, const int* offsets, const float* xs,
-                         int n_buckets, int d, int k, int metric, cudaStream_t st);
+                         long long n_rows, int n_buckets, int d, int k, int metric, cudaStream_t st);
 int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st);
