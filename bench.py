@@ -338,14 +338,18 @@ def run_b200(args):
     achieved = algo_bytes / (scan_avg_ms * 1e-3) / 1e9
     mean_cand = float(ncand_local.double().mean().item())
 
-    traffic = None
-    prof_path = os.path.join(ROOT, "profiles", "ncu_scan_traffic.json")
-    if os.path.exists(prof_path):
-        rec = json.load(open(prof_path)).get(f"{args.workload}/p{p_used}/gpus{world}")
-        traffic = rec["dram_bytes_per_launch"] if rec else None
     qps = nq * args.steps / (ms * 1e-3)
     e2e_qps = nq * args.steps / (e2e_ms * 1e-3)
     scan_impl = _native.scan_impl(d, k, index.local._metric, index.local._x_sqnorm is not None)
+    traffic = None
+    prof_path = os.path.join(ROOT, "profiles", "ncu_scan_traffic.json")
+    if os.path.exists(prof_path):
+        rec = json.load(open(prof_path)).get(
+            f"{args.workload}/p{p_used}/gpus{world}/{'tc' if scan_impl == 1 else 'simt'}")
+        traffic = rec["dram_bytes_per_launch"] if rec else None
+    # bytes of the DISTINCT buckets the batch probes: what HBM has to deliver at least once per step
+    all_probes = index.local.hash_tensors(Q, p_used)
+    distinct = float(lr_sizes[torch.unique(all_probes[all_probes >= 0]).long()].sum().item()) * (4 * d + 4)
     scan_kernel_name = ("scan_tc_kernel (tcgen05 tf32 filter + exact fp32 re-rank + top-k)" if scan_impl == 1
                         else "scan_kernel (fp32 SIMT candidate scan + top-k)")
     line = {
@@ -372,8 +376,14 @@ def run_b200(args):
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": scan_avg_ms,
                      "kernel_share_of_step": scan_avg_ms / (ms / args.steps),
+                     "distinct_bucket_bytes": distinct,
+                     "achieved_distinct": distinct / (scan_avg_ms * 1e-3) / 1e9,
+                     "frac_distinct": distinct / (scan_avg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "dram_gbs": (traffic / (scan_avg_ms * 1e-3) / 1e9) if traffic else None,
                      "note": "algorithmic bytes count every (query, candidate) pair; a bucket tile "
-                             "shared by several queries is fetched once, so achieved may exceed peak",
+                             "shared by several queries is fetched once, so achieved may exceed peak; "
+                             "*_distinct counts every probed bucket once (the bytes HBM must deliver), "
+                             "dram_gbs is ncu's dram__bytes per launch over the live kernel time",
                      "fp32_lane_ops_frac": (float(ncand_local.double().sum().item()) * d * (3 if metric == "l2" else 1))
                      / (scan_avg_ms * 1e-3) / (torch.cuda.get_device_properties(device).multi_processor_count
                                                * 128 * clocks.get("sm_max_mhz", 1965.0) * 1e6

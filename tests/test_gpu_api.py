@@ -181,3 +181,50 @@ def test_packed_exchange_buffer_and_strided_merge(oracle):
     o_ids, o_d = oracle.merge_topk(all_d.numpy(), all_i.numpy(), k)
     assert np.array_equal(m_ids.cpu().numpy(), o_ids) and np.array_equal(m_d.cpu().numpy(), o_d)
     assert torch.equal(m_n.cpu(), all_n.sum(0).int())
+
+
+def test_validation_block_and_recall_sweep(oracle):
+    """the Trainer.fit validation block (base.py:80-115) and the eval.py sweep,
+    driven through the CUDA Indexer; recall must equal metrics.py on the oracle's CPU flow."""
+    import precompute
+    from encoders import MultiLayerRelu
+    from helpers import mixture, oracle_layers_from_hashing
+    from nlsh.evaluation import recall_sweep, validate_index
+    from nlsh.hashings import MultivariateBernoulli
+    from nlsh.metrics import calculate_recall
+    torch.manual_seed(3)
+    X = mixture(30000, 64, 48, seed=5)
+    Q = mixture(400, 64, 48, seed=5) + 0.05 * torch.randn(400, 64, generator=torch.Generator().manual_seed(1))
+    h = MultivariateBernoulli(MultiLayerRelu(64, [64, 64]), 6, F.pairwise_distance)
+    gt, _ = precompute.knn_tensors(Q.cuda(), X.cuda(), "l2", 10)
+
+    class Log:
+        def __init__(self):
+            self.rows = {}
+
+        def log(self, name, value, step):
+            self.rows[name] = (value, step)
+
+    log = Log()
+    res = validate_index(h, X.cuda(), F.pairwise_distance, Q.cuda(), gt.cpu().numpy(), k=10, hash_times=4,
+                         logger=log, global_step=300)
+    assert set(log.rows) == {"test/n_indexes", "test/std_index_rows", "test/recall", "test/query_size", "test/qps"}
+    assert log.rows["test/recall"][1] == 300 and res["test/qps"] > 0
+    idx = res["indexer"]
+    # the same numbers from the reference's flow on the CPU (oracle), fed the same probe sets
+    probes = idx.hash_tensors(Q.cuda(), 4).cpu().numpy()
+    sets = [set(int(c) for c in row if c >= 0) for row in probes]
+    index2row = {int(c): idx.index2row[c].cpu().numpy() for c in idx.index2row}
+    o_ids, _, o_n = oracle.query(X, index2row, Q, sets, "l2", 10)
+    want = calculate_recall(gt.cpu().tolist(), o_ids, np.mean)
+    assert res["test/recall"] == pytest.approx(want, abs=1e-9)
+    assert res["test/query_size"] == pytest.approx(float(np.mean(o_n)))
+    assert res["test/n_indexes"] == len(index2row)
+    fast = validate_index(h, X.cuda(), F.pairwise_distance, Q.cuda(), gt.cpu().numpy(), k=10, hash_times=4,
+                          list_api=False)
+    assert fast["test/recall"] == pytest.approx(want, abs=1e-6)
+    rows = recall_sweep(idx, Q.cuda(), gt.cpu().numpy(), k=10, probe_counts=(1, 2, 4, 8, 128))
+    assert [r["probes"] for r in rows] == [1, 2, 4, 8]
+    assert all(b["recall"] >= a["recall"] - 1e-9 and b["avg_n_candidates"] >= a["avg_n_candidates"]
+               for a, b in zip(rows, rows[1:]))
+    assert rows[2]["recall"] == pytest.approx(want, abs=1e-6)
