@@ -340,7 +340,7 @@ def run_b200(args):
 
     qps = nq * args.steps / (ms * 1e-3)
     e2e_qps = nq * args.steps / (e2e_ms * 1e-3)
-    scan_impl = _native.scan_impl(d, k, index.local._metric, index.local._x_sqnorm is not None)
+    scan_impl = _native.scan_impl(d, k, index.local._metric, index.local._x_sqnorm is not None, nq, p_used, 1 << hs)
     traffic = None
     prof_path = os.path.join(ROOT, "profiles", "ncu_scan_traffic.json")
     if os.path.exists(prof_path):
@@ -389,6 +389,9 @@ def run_b200(args):
                                                * 128 * clocks.get("sm_max_mhz", 1965.0) * 1e6
                                                if clocks.get("sm_max_mhz") else 148 * 128 * 1.965e9),
                      "hbm_bound_case": {"queries": n_lr, "probes": p_used, "kernel_ms": lr_avg_ms,
+                                        "kernel": "scan_tc_kernel" if _native.scan_impl(
+                                            d, k, index.local._metric, index.local._x_sqnorm is not None, n_lr,
+                                            p_used, 1 << hs) == 1 else "scan_kernel (fp32 SIMT)",
                                         "algorithmic_bytes_per_launch": lr_bytes,
                                         "achieved": lr_bytes / (lr_avg_ms * 1e-3) / 1e9,
                                         "frac": lr_bytes / (lr_avg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],

@@ -164,9 +164,11 @@ int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t d, const in
                          float* dists_out, int32_t* ncand_out, void* workspace,
                          size_t workspace_bytes, uint32_t flags, void* stream);
 
-/* Which kernel nlsh_query_scan_topk runs for (d, k, metric) with / without x_sqnorm and default
- * flags: 1 = tensor-core filtered scan (scan_tc.cu), 0 = fp32 SIMT scan (scan.cu). */
-int nlsh_query_scan_impl(int32_t d, int32_t k, int32_t metric, int32_t has_sqnorm);
+/* Which kernel nlsh_query_scan_topk runs for this shape with / without x_sqnorm and default flags:
+ * 1 = tensor-core filtered scan (scan_tc.cu: d <= 128, k <= 32 and at least ~4 (query, probe) pairs
+ * per bucket, i.e. bucket tiles are shared between queries), 0 = fp32 SIMT scan (scan.cu). */
+int nlsh_query_scan_impl(int32_t d, int32_t k, int32_t metric, int32_t has_sqnorm, int64_t n_queries,
+                         int32_t p, int32_t n_buckets);
 
 /* ---------------------------------------------------------------------------------------
  * Brute-force kNN (ground truth / training labels).

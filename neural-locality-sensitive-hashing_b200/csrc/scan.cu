@@ -1132,8 +1132,20 @@ bool scan_use_tc(int d, int k, int metric) {
 }
 }  // namespace
 
-extern "C" int nlsh_query_scan_impl(int32_t d, int32_t k, int32_t metric, int32_t has_sqnorm) {
-  return (has_sqnorm && scan_use_tc(d, k, metric)) ? 1 : 0;
+namespace {
+// The tensor-core filter pays off when a bucket tile serves several queries (one GEMM tile scores
+// 32 of them); with about one query per probed bucket the fp32 SIMT kernel already streams at the
+// HBM rate (0.94 of the copy peak) and has no seed / re-rank stages, so it keeps those batches.
+bool scan_batch_prefers_tc(int64_t n_queries, int32_t p, int32_t n_buckets) {
+  const char* env = getenv("NLSH_SCAN_IMPL");
+  if (env != nullptr && strcmp(env, "tc") == 0) return true;
+  return n_queries * (int64_t)p >= 4 * (int64_t)n_buckets;
+}
+}  // namespace
+
+extern "C" int nlsh_query_scan_impl(int32_t d, int32_t k, int32_t metric, int32_t has_sqnorm,
+                                    int64_t n_queries, int32_t p, int32_t n_buckets) {
+  return (has_sqnorm && scan_use_tc(d, k, metric) && scan_batch_prefers_tc(n_queries, p, n_buckets)) ? 1 : 0;
 }
 
 extern "C" size_t nlsh_query_workspace_bytes(int64_t n_queries, int32_t p, int32_t k, int32_t d,
@@ -1185,7 +1197,8 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   const bool async = (flags & 1u) == 0;
   // tensor-core filtered scan (scan_tc.cu) whenever the index carries the row norms
   const bool use_tc = tc_sized && async && (flags & 2u) == 0 && x_sqnorm != nullptr && n_rows > 0 &&
-                      (reinterpret_cast<uintptr_t>(x_sqnorm) & 15) == 0 && scan_use_tc(d, k, metric);
+                      (reinterpret_cast<uintptr_t>(x_sqnorm) & 15) == 0 && scan_use_tc(d, k, metric) &&
+                      scan_batch_prefers_tc(n_queries, p, n_buckets);
   const ScanPolicy pol = use_tc ? pol_tc : pol_simt;
   const ScanGeom geom = scan_geom(d, k, async);
   const long long n_pairs = (long long)n_queries * p;

@@ -60,7 +60,7 @@ PROTOTYPES = {
     "nlsh_query_scan_topk": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64,
                                             _i64, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _u32,
                                             _vp]),
-    "nlsh_query_scan_impl": (ctypes.c_int, [_i32, _i32, _i32, _i32]),
+    "nlsh_query_scan_impl": (ctypes.c_int, [_i32, _i32, _i32, _i32, _i64, _i32, _i32]),
     "nlsh_knn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "nlsh_knn_bruteforce": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _i64,
                                            _vp, _vp, _vp, _sz, _vp]),
@@ -317,9 +317,9 @@ def query_scan_topk(xq, probes, offsets, ids, x_sorted, d, max_bucket_rows, metr
     return out_ids, out_d, out_n
 
 
-def scan_impl(d, k, metric, has_sqnorm=True):
+def scan_impl(d, k, metric, has_sqnorm=True, n_queries=1 << 20, p=1, n_buckets=1):
     """Which scan kernel nlsh_query_scan_topk runs for this shape: 1 = tensor-core filtered, 0 = fp32 SIMT."""
-    return int(lib().nlsh_query_scan_impl(d, k, metric, 1 if has_sqnorm else 0))
+    return int(lib().nlsh_query_scan_impl(d, k, metric, 1 if has_sqnorm else 0, n_queries, p, n_buckets))
 
 
 def knn_bruteforce(xq, xdb, metric, k, exclude_self=False, self_offset=0, id_offset=0):

@@ -12,6 +12,17 @@ pytestmark = pytest.mark.gpu
 ANGULAR_ATOL = 2e-6  # 1 - cos cancels near 0
 
 
+@pytest.fixture(autouse=True, params=["auto", "tc"])
+def scan_impl(request, monkeypatch):
+    """Every test of this file runs twice: with the library's own choice of scan kernel (small
+    batches go to the fp32 SIMT kernel) and with the tensor-core filtered kernel forced."""
+    if request.param == "tc":
+        monkeypatch.setenv("NLSH_SCAN_IMPL", "tc")
+    else:
+        monkeypatch.delenv("NLSH_SCAN_IMPL", raising=False)
+    return request.param
+
+
 def lists(ids, dists):
     ids, dists = ids.cpu().numpy(), dists.cpu().numpy()
     out_i, out_d = [], []
@@ -113,12 +124,13 @@ def test_query_against_oracle(oracle, n, d, hs, nq, p, k, metric):
     (40_000, 8, 4, 300, 2, 10, "angular", "duplicates"),
     (3000, 128, 2, 5000, 2, 10, "l2", "mixture"),        # far more queries than rows per bucket
 ])
-def test_tensor_core_filter_is_exact(n, d, hs, nq, p, k, metric, kind):
+def test_tensor_core_filter_is_exact(monkeypatch, n, d, hs, nq, p, k, metric, kind):
     """scan_tc.cu (tcgen05 tf32 GEMM as a filter + exact re-rank) must return bit-for-bit what the
     fp32 SIMT scan kernel returns: a pair the filter dropped wrongly would show up here."""
     from encoders import MultiLayerRelu
     from nlsh.hashings import MultivariateBernoulli
     from nlsh.indexer import Indexer
+    monkeypatch.setenv("NLSH_SCAN_IMPL", "tc")  # also where the library would pick the SIMT kernel by itself
     torch.manual_seed(n + d + hs)
     X = mixture(n, d, 3 << hs, seed=n)
     Q = mixture(nq, d, 3 << hs, seed=n) + 0.1 * torch.randn(nq, d, generator=torch.Generator().manual_seed(7))
