@@ -111,10 +111,18 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-f", self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100", "-f", self.path],
+                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+
+    def count(self):
+        """Samples written so far."""
+        try:
+            return sum(1 for line in open(self.path) if line.strip())
+        except (OSError, TypeError):
+            return 0
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -325,6 +333,13 @@ def run_b200(args):
         _, _, ncand_lr = index.local.query_tensors(Q[:n_lr], k=k, hash_times=p_used)
     lr_ms = _native.profile_read()
     _native.profile_enable(False)
+    # nvidia-smi needs about a second to deliver its first sample; short runs (a 0.8 ms step x 50)
+    # would end before it: keep the same query step running, untimed, until a few samples exist
+    t_load = time.perf_counter()
+    while sampler.proc is not None and sampler.count() < 3 and time.perf_counter() - t_load < 6.0:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
     clocks = sampler.stop()
     lr_bytes = float(ncand_lr.double().sum().item()) * (4 * d + 4) + n_lr * (4 * d + 8 * k)
     # bytes of the DISTINCT buckets those queries probe: what has to come from HBM at least once
