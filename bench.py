@@ -335,9 +335,10 @@ def run_b200(args):
     _native.profile_enable(False)
     # nvidia-smi needs about a second to deliver its first sample; short runs (a 0.8 ms step x 50)
     # would end before it: keep the same query step running, untimed, until a few samples exist
-    t_load = time.perf_counter()
-    while sampler.proc is not None and sampler.count() < 3 and time.perf_counter() - t_load < 6.0:
-        for _ in range(50):
+    # (a fixed number of steps derived from the rank-maximum step time, so that every rank issues the
+    # same number of all-gathers)
+    if sampler.proc is not None:
+        for _ in range(int(min(20000, max(0.0, 1500.0 / max(ms / args.steps, 1e-3))))):
             step()
         torch.cuda.synchronize()
     clocks = sampler.stop()
