@@ -113,3 +113,58 @@ class ShardedIndexer:
         ids, _, ncand = self.query_tensors(query_vectors, k, hash_times, probes)
         rows = ids.cpu().tolist()
         return [[v for v in r if v >= 0] for r in rows], ncand.cpu().tolist()
+
+
+class PipelinedSearch:
+    """Host-to-host serving loop over a captured query graph (ShardedIndexer.capture_query) for a
+    fixed batch shape: pinned host queries in, pinned host results out, `depth` batches in flight.
+    The host-to-device copy of batch i+1 runs on a side stream while batch i is searched; the
+    device-to-host copies of a batch's results follow its search on the main stream.
+
+        pipe = PipelinedSearch(index, n_queries, k=10, hash_times=8)
+        t = pipe.submit(q_pinned)              # enqueue; returns a ticket, does not block
+        ids, dists, ncand = pipe.result(t)     # blocks until that batch's results are on the host
+                                               # (pinned buffers, reused `depth` submits later)
+    """
+
+    def __init__(self, sharded_index, n_queries, k=10, hash_times=10, depth=2):
+        local = sharded_index.local
+        dev = local._candidate_vectors_gpu.device
+        self.run = sharded_index.capture_query(n_queries, k=k, hash_times=hash_times)
+        self.depth = int(depth)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.q_dev = [torch.empty((n_queries, local._dim), dtype=torch.float32, device=dev)
+                      for _ in range(self.depth)]
+        self.out = [(torch.empty((n_queries, k), dtype=torch.int64).pin_memory(),
+                     torch.empty((n_queries, k), dtype=torch.float32).pin_memory(),
+                     torch.empty((n_queries,), dtype=torch.int32).pin_memory()) for _ in range(self.depth)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.consumed = [torch.cuda.Event() for _ in range(self.depth)]
+        self.d2h_done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.submitted = 0
+        self.h2d_bytes = n_queries * local._dim * 4
+        self.d2h_bytes = n_queries * k * 12 + n_queries * 4
+        self.kernels_per_call = getattr(self.run, "kernels_per_call", None)
+
+    def submit(self, q_pinned):
+        s = self.submitted % self.depth
+        main = torch.cuda.current_stream(self.q_dev[s].device)
+        if self.submitted >= self.depth:
+            self.copy_stream.wait_event(self.consumed[s])  # the slot's previous search has read q_dev[s]
+        with torch.cuda.stream(self.copy_stream):
+            self.q_dev[s].copy_(q_pinned, non_blocking=True)
+            self.h2d_done[s].record(self.copy_stream)
+        main.wait_event(self.h2d_done[s])
+        ids, dists, ncand = self.run(self.q_dev[s])
+        self.consumed[s].record(main)
+        o_ids, o_d, o_n = self.out[s]
+        o_ids.copy_(ids, non_blocking=True)
+        o_d.copy_(dists, non_blocking=True)
+        o_n.copy_(ncand, non_blocking=True)
+        self.d2h_done[s].record(main)
+        self.submitted += 1
+        return s
+
+    def result(self, ticket):
+        self.d2h_done[ticket].synchronize()
+        return self.out[ticket]

@@ -228,3 +228,30 @@ def test_validation_block_and_recall_sweep(oracle):
     assert all(b["recall"] >= a["recall"] - 1e-9 and b["avg_n_candidates"] >= a["avg_n_candidates"]
                for a, b in zip(rows, rows[1:]))
     assert rows[2]["recall"] == pytest.approx(want, abs=1e-6)
+
+
+def test_pipelined_search_matches_direct_calls():
+    """nlsh.parallel.PipelinedSearch: double-buffered host-to-host loop == direct query_tensors calls."""
+    from encoders import MultiLayerRelu
+    from nlsh.hashings import MultivariateBernoulli
+    from nlsh.parallel import PipelinedSearch, ShardedIndexer
+    torch.manual_seed(5)
+    X = mixture(40000, 32, 40, seed=9)
+    h = MultivariateBernoulli(MultiLayerRelu(32, [64]), 5, F.pairwise_distance)
+    h.train_mode(False)
+    index = ShardedIndexer(h, X.cuda(), F.pairwise_distance, shard_lo=0)
+    nq, k, p = 512, 10, 4
+    batches = [(mixture(nq, 32, 40, seed=9) + 0.01 * i).pin_memory() for i in range(5)]
+    pipe = PipelinedSearch(index, nq, k=k, hash_times=p)
+    tickets, got = [], []
+    for b in batches:
+        tickets.append(pipe.submit(b))
+        if len(tickets) > 1:
+            ids, dists, ncand = pipe.result(tickets.pop(0))
+            got.append((ids.clone(), dists.clone(), ncand.clone()))
+    ids, dists, ncand = pipe.result(tickets.pop(0))
+    got.append((ids.clone(), dists.clone(), ncand.clone()))
+    assert len(got) == len(batches)
+    for b, (ids, dists, ncand) in zip(batches, got):
+        w_ids, w_d, w_n = index.query_tensors(b.cuda(), k=k, hash_times=p)
+        assert torch.equal(ids, w_ids.cpu()) and torch.equal(dists, w_d.cpu()) and torch.equal(ncand, w_n.cpu())
