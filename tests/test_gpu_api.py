@@ -255,3 +255,38 @@ def test_pipelined_search_matches_direct_calls():
     for b, (ids, dists, ncand) in zip(batches, got):
         w_ids, w_d, w_n = index.query_tensors(b.cuda(), k=k, hash_times=p)
         assert torch.equal(ids, w_ids.cpu()) and torch.equal(dists, w_d.cpu()) and torch.equal(ncand, w_n.cpu())
+
+
+def test_full_size_config4_filter_equals_simt():
+    """BASELINE config 4 at full size on one GPU (10M x 128, 4096 buckets, 10k queries, p = 8, k = 10):
+    the tensor-core filtered scan and the fp32 SIMT scan must return identical bits, every id must be
+    a row of a probed bucket, and the candidate counts must be the probed buckets' sizes."""
+    import synth
+    from encoders import MultiLayerRelu
+    from nlsh import _native
+    from nlsh.hashings import MultivariateBernoulli
+    from nlsh.indexer import Indexer
+    n, d, hs, nq, k, p = 10_000_000, 128, 12, 10_000, 10, 8
+    dev = torch.device("cuda")
+    X = synth.make_database(n, d, hs, 1004, dev)
+    Q = synth.make_queries(nq, d, hs, 1004, dev)
+    torch.manual_seed(1004)
+    hashing = MultivariateBernoulli(MultiLayerRelu(d, [256, 256]), hs, F.pairwise_distance)
+    synth.fit_hasher(hashing, d, hs, 1004, dev, steps=60)
+    idx = Indexer(hashing, X, F.pairwise_distance)
+    assert _native.scan_impl(d, k, idx._metric, True, nq, p, 1 << hs) == 1
+    probes = idx.hash_tensors(Q, p)
+    ids, dists, ncand = idx.query_tensors(Q, k=k, probes=probes)
+    idx.scan_flags = 2  # fp32 SIMT kernel
+    ids2, dists2, ncand2 = idx.query_tensors(Q, k=k, probes=probes)
+    assert torch.equal(ids, ids2) and torch.equal(dists, dists2) and torch.equal(ncand, ncand2)
+    sizes = torch.from_numpy(idx.bucket_sizes).to(dev)
+    assert torch.equal(ncand.long(), sizes[probes.long()].sum(1))
+    sample = torch.arange(0, nq, 10, device=dev)
+    got = ids[sample]
+    exact = F.pairwise_distance(Q[sample][:, None, :].expand(-1, k, -1).reshape(-1, d),
+                                X[got.reshape(-1)]).view(-1, k)
+    torch.testing.assert_close(dists[sample], exact, rtol=1e-5, atol=0)
+    codes_of_ids = hashing.hash_tensors(X[got.reshape(-1)], 1)[0].view(-1, k)
+    assert (codes_of_ids[:, :, None] == probes[sample][:, None, :]).any(-1).all()
+    assert (dists[:, 1:] >= dists[:, :-1]).all()
