@@ -38,6 +38,8 @@ constexpr int kKnMaxCGroups = 4;
 constexpr int kKnMaxThreads = 64 + 128 * kKnMaxCGroups;
 constexpr int kKnHeapCap = NLSH_MAX_K;
 constexpr int kKnLocalHeapK = 16;  // largest k whose heaps live in thread-local memory
+constexpr int kKnCandBuf = 32;     // per-thread candidate buffer (shared-memory heaps only), flushed
+                                   // warp-wide so the 32 lanes sift their heaps at the same time
 constexpr uint32_t kKnStageBytes = 2u * kKnBN * kTcBK * sizeof(float);  // 16 KB
 
 struct KnnTcArgs {
@@ -126,6 +128,8 @@ __global__ void __launch_bounds__(kKnMaxThreads, 1)
   float* heap_d_s = reinterpret_cast<float*>(tmem_slot + 4);  // [k][epilogue threads] when k > kKnLocalHeapK
   const int n_epi = 128 * a.cgroups;
   int* heap_id_s = reinterpret_cast<int*>(heap_d_s + (size_t)a.k * n_epi);
+  float* cand_d_s = reinterpret_cast<float*>(heap_id_s + (size_t)a.k * n_epi);  // [kKnCandBuf][epilogue threads]
+  int* cand_id_s = reinterpret_cast<int*>(cand_d_s + (size_t)kKnCandBuf * n_epi);
 
   // warp 0: TMA producer; warp 1: MMA issuer + TMEM owner; warps 2 .. 2 + 4 * cgroups: epilogue
   const int tid = threadIdx.x;
@@ -256,6 +260,10 @@ __global__ void __launch_bounds__(kKnMaxThreads, 1)
       heap.id = heap_id_s + (tid - 64);
       heap.stride = n_epi;
     }
+    const bool buffered = a.k > kKnLocalHeapK;
+    float* cand_d = cand_d_s + (tid - 64);
+    int* cand_i = cand_id_s + (tid - 64);
+    int n_cand = 0;
     // a thread without a query never passes the filter
     float tau = q_ok ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
     int tau_id = NLSH_ID_SENTINEL;
@@ -298,7 +306,32 @@ __global__ void __launch_bounds__(kKnMaxThreads, 1)
             if (dist[i] <= tau) {
               const int row = row0 + c0 + i;
               if (row < a.n_rows && row != self_row && TopHeap::less(dist[i], row, tau, tau_id)) {
-                heap.push(dist[i], row, a.k);
+                if (buffered) {  // park it: the heap is updated by the warp-wide flush below
+                  cand_d[n_cand * n_epi] = dist[i];
+                  cand_i[n_cand * n_epi] = row;
+                  ++n_cand;
+                } else {
+                  heap.push(dist[i], row, a.k);
+                  if (heap.n == a.k) {
+                    tau = heap.d[0];
+                    tau_id = heap.id[0];
+                  }
+                }
+              }
+            }
+          }
+        }
+        // Large k: a push is ~7 dependent sift levels through shared memory; one lane pushing while
+        // 31 wait cost 850 cycles per candidate.  Parked candidates are pushed by all lanes together
+        // whenever some lane's buffer could overflow on the next 16 scores.
+        if (buffered && __any_sync(NLSH_FULL_MASK, n_cand > kKnCandBuf - 16)) {
+          const int rounds = __reduce_max_sync(NLSH_FULL_MASK, n_cand);
+          for (int e = 0; e < rounds; ++e) {
+            if (e < n_cand) {
+              const float cd = cand_d[e * n_epi];
+              const int ci = cand_i[e * n_epi];
+              if (TopHeap::less(cd, ci, tau, tau_id)) {
+                heap.push(cd, ci, a.k);
                 if (heap.n == a.k) {
                   tau = heap.d[0];
                   tau_id = heap.id[0];
@@ -306,11 +339,23 @@ __global__ void __launch_bounds__(kKnMaxThreads, 1)
               }
             }
           }
+          n_cand = 0;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[set]);
+    }
+    for (int e = 0; e < n_cand; ++e) {  // whatever is still parked
+      const float cd = cand_d[e * n_epi];
+      const int ci = cand_i[e * n_epi];
+      if (TopHeap::less(cd, ci, tau, tau_id)) {
+        heap.push(cd, ci, a.k);
+        if (heap.n == a.k) {
+          tau = heap.d[0];
+          tau_id = heap.id[0];
+        }
+      }
     }
     if (q_ok) {
       const size_t slot = (((size_t)my_q * a.n_blocks + a.block0 + split) * a.cgroups + cg) * a.k;
@@ -418,7 +463,7 @@ int nlsh_knn_tc_run(const float* xq, long long n_queries, const float* xdb, long
   float* x_lo = x_hi + (size_t)p.chunk_rows * d;
   float* term = x_lo + (size_t)p.chunk_rows * d;
   const int cgroups = knn_tc_cgroups(k);
-  const size_t heap_bytes = k > kKnLocalHeapK ? (size_t)k * 128 * cgroups * 8 : 0;
+  const size_t heap_bytes = k > kKnLocalHeapK ? (size_t)(k + kKnCandBuf) * 128 * cgroups * 8 : 0;
   const size_t fixed = kKnNormSlots * kKnBN * sizeof(float) + 512 + 1024 + heap_bytes;
   int stages = kKnStages;
   while (stages > 3 && stages * (size_t)kKnStageBytes + fixed > 222 * 1024) --stages;
