@@ -90,3 +90,29 @@ DISTANCE_FUNC = {
     "glove_200": _cosine_distance,
     "sift": _l2,
 }
+
+
+def nearest_exclude_positive(vectors, distance_function, positive_indexes):
+    """Negative mining of the triplet trainer (nlsh/trainers/triplet.py:44-74): for every row the
+    index of the nearest row that is neither the row itself nor one of its `positive_indexes`
+    [n, kp].  The reference materialises a 32 x n distance matrix per batch and masks it; here one
+    fused kNN call asks for kp + 2 neighbours (self + kp positives + one more can never all be
+    excluded) and the first admissible one is picked.  `distance_function` is a pairwise-matrix
+    function of the reference (`_l2` / `_cosine_distance` / `Glove.pairwise_distance`) or a metric
+    name.  Returns a LongTensor [n] on the device."""
+    if not vectors.is_cuda:
+        raise _native.NativeLibraryError("nearest_exclude_positive needs CUDA tensors (no CPU fallback)")
+    n = vectors.shape[0]
+    positive_indexes = positive_indexes.to(vectors.device).long().reshape(n, -1)
+    kp = positive_indexes.shape[1]
+    kk = min(kp + 2, n)
+    if kk > _native.MAX_K:
+        raise ValueError(f"nearest_exclude_positive: {kp} positives per row exceed the top-k capacity")
+    ids, _ = knn_tensors(vectors, vectors, distance_function, kk)
+    own = torch.arange(n, device=vectors.device)[:, None]
+    excluded = (ids == own) | (ids[:, :, None] == positive_indexes[:, None, :]).any(-1) | (ids < 0)
+    first = (~excluded).float().argmax(dim=1)  # first admissible neighbour (ids are sorted by distance)
+    out = ids.gather(1, first[:, None]).squeeze(1)
+    if excluded.all(dim=1).any():
+        raise ValueError("nearest_exclude_positive: a row has no admissible neighbour")
+    return out

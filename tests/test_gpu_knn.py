@@ -144,3 +144,25 @@ def test_recall_kernel_matches_metrics():
     pred[5, 3:] = -1
     want = calculate_recall(gt.tolist(), [[v for v in r if v >= 0] for r in pred.tolist()], np.mean)
     assert recall_at_k_tensors(gt.cuda(), pred.cuda()) == pytest.approx(want)
+
+
+@pytest.mark.parametrize("metric_fn", ["_l2", "_cosine_distance"])
+def test_nearest_exclude_positive_matches_reference_loop(metric_fn):
+    """nlsh/trainers/triplet.py:44-74 restated densely: mask self + positives, argmin."""
+    import precompute
+    fn = getattr(precompute, metric_fn)
+    g = torch.Generator().manual_seed(3)
+    V = torch.randn(700, 24, generator=g).cuda()
+    pos = precompute.knn_tensors(V, V, fn, 6, exclude_self=True)[0][:, :5]  # 5 positives per row
+    got = precompute.nearest_exclude_positive(V, fn, pos)
+    dist = fn(V, V)
+    dist.scatter_(1, pos, float("inf"))
+    dist.fill_diagonal_(float("inf"))
+    want = dist.argmin(dim=1)
+    same = (got == want)
+    if not same.all():  # only where the two nearest admissible rows tie within rounding
+        rows = (~same).nonzero().squeeze(1)
+        d2 = fn(V, V)
+        assert torch.allclose(d2[rows, got[rows]], d2[rows, want[rows]], rtol=1e-4, atol=1e-6)
+    assert same.float().mean() > 0.99
+    assert not (got[:, None] == pos).any() and not (got == torch.arange(700, device="cuda")).any()

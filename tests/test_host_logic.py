@@ -129,3 +129,23 @@ def test_precompute_metric_resolution():
         precompute._resolve_knn_metric(lambda a, b: a @ b.T)
     a, b = torch.randn(5, 7), torch.randn(6, 7)
     torch.testing.assert_close(precompute._l2(a, b), torch.cdist(a, b) ** 2, rtol=1e-4, atol=1e-4)
+
+
+def test_vecs_round_trip(tmp_path):
+    from nlsh.data_io import load_dataset, read_vecs, save_processed, write_vecs
+    rng = np.random.RandomState(0)
+    f = rng.randn(37, 16).astype(np.float32)
+    i = rng.randint(0, 1000, size=(37, 5)).astype(np.int32)
+    b = rng.randint(0, 256, size=(9, 128)).astype(np.uint8)
+    for name, arr in (("train.fvecs", f), ("neighbors.ivecs", i), ("x.bvecs", b)):
+        write_vecs(str(tmp_path / name), arr)
+        assert np.array_equal(read_vecs(str(tmp_path / name)), arr)
+    assert read_vecs(str(tmp_path / "train.fvecs"), max_rows=10).shape == (10, 16)
+    np.save(tmp_path / "test.npy", f[:5])
+    ds = load_dataset(str(tmp_path))
+    assert set(ds) == {"train", "test", "neighbors"} and np.array_equal(ds["test"], f[:5])
+    save_processed(str(tmp_path), i)
+    assert np.array_equal(load_dataset(str(tmp_path))["train_knn"], i)
+    (tmp_path / "bad.fvecs").write_bytes(b"\x03\x00\x00\x00abc")
+    with pytest.raises(ValueError):
+        read_vecs(str(tmp_path / "bad.fvecs"))
