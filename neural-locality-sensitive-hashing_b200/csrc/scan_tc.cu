@@ -77,7 +77,7 @@ namespace {
 
 constexpr int kFilterWarps = 4;                 // one per TMEM lane quarter
 constexpr int kRerankWarps = 8;                 // two per scheduler: their latencies overlap
-constexpr int kRerankShift = 3;                 // log2(kRerankWarps)
+constexpr int kRerankShift = 3;                 // log2(kRerankWarps): query j belongs to warp j & 7, list j >> 3
 constexpr int kTile = 128;                      // rows per tile = UMMA M
 constexpr int kThreads = 64 + 32 * (kFilterWarps + kRerankWarps);  // 320
 constexpr int kOwn = kTcNQ / kRerankWarps;      // lists per re-rank warp
