@@ -123,6 +123,9 @@ def test_query_against_oracle(oracle, n, d, hs, nq, p, k, metric):
     (40_000, 30, 4, 300, 2, 7, "l2", "duplicates"),      # exact ties -> (distance, id) order; d % 4 != 0
     (40_000, 8, 4, 300, 2, 10, "angular", "duplicates"),
     (3000, 128, 2, 5000, 2, 10, "l2", "mixture"),        # far more queries than rows per bucket
+    (30001, 128, 5, 600, 3, 10, "l2", "mixture"),        # row count not a multiple of 4: the last rows' norms
+    (9999, 64, 3, 500, 2, 10, "angular", "mixture"),     # are read outside the 16-byte aligned bulk copies
+    (777, 16, 1, 300, 2, 32, "l2", "mixture"),           # two buckets of a few tiles, k = 32
 ])
 def test_tensor_core_filter_is_exact(monkeypatch, n, d, hs, nq, p, k, metric, kind):
     """scan_tc.cu (tcgen05 tf32 GEMM as a filter + exact re-rank) must return bit-for-bit what the
