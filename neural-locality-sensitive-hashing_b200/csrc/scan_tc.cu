@@ -675,12 +675,13 @@ int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, 
   gather_pair_queries_kernel<<<(unsigned)blocks, 256, 0, st>>>(qn, pairs, n_valid, n_pairs, p, d_pad, qs,
                                                              qs_norm, tau_g, n_queries);
   NLSH_CUDA_TRY(nlsh_post_launch());
-  // rows sampled per bucket: half of the average bucket, between 32 and 128
+  // rows sampled per bucket: half of the average bucket, between 32 and 128 (256 for big buckets)
   // (NLSH_SCAN_SEED=<rows> overrides; 0 = no seeding, for A/B runs)
   const long long avg = n_buckets > 0 ? n_rows / n_buckets : 0;
   int seed_rows = (int)(avg / 2 / 32 * 32);
   if (seed_rows < 32) seed_rows = 32;
   if (seed_rows > 128) seed_rows = 128;
+  if (avg >= 2048) seed_rows = 256;  // big buckets: the tighter start pays for the larger sample (measured)
   if (const char* env = getenv("NLSH_SCAN_SEED")) seed_rows = atoi(env);
   if (seed_rows <= 0) return NLSH_OK;
   if (seed_rows > kMaxSeedRows) seed_rows = kMaxSeedRows;
