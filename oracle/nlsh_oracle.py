@@ -270,6 +270,24 @@ def knn_queries(queries, vectors, metric: str, k: int, batch_size: int = 512):
 # ---------------------------------------------------------------------------------------
 # multi-GPU merge (no reference counterpart)
 # ---------------------------------------------------------------------------------------
+def nearest_exclude_positive(vectors, metric: str, positive_indexes, batch_size: int = 32) -> torch.Tensor:
+    """nlsh/trainers/triplet.py:44-74: per batch of rows the full distance matrix, the row's positives
+    and the row itself overwritten with the matrix maximum, then argmin (the `.cuda()` calls dropped)."""
+    vectors = torch.as_tensor(vectors, dtype=torch.float32)
+    positive_indexes = torch.as_tensor(positive_indexes, dtype=torch.int64)
+    n = vectors.shape[0]
+    out = []
+    for start in range(0, n, batch_size):  # the reference's separate last-batch branch does the same
+        batch = vectors[start:start + batch_size]
+        distances = knn_distance_matrix(batch, vectors, metric).clone()
+        max_value = float(distances.max())  # (the reference passes the 0-d tensor; torch 2 wants the scalar overload)
+        distances.scatter_(1, positive_indexes[start:start + batch_size], max_value)
+        diag = torch.arange(start, start + batch.shape[0]).reshape(-1, 1)
+        distances.scatter_(1, diag, max_value)  # don't select self
+        out.append(distances.argmin(dim=1))
+    return torch.cat(out)
+
+
 def merge_topk(dists, ids, k: int):
     """[NO REFERENCE COUNTERPART] k smallest (distance, id) pairs over G per-shard lists
     [G, Q, k]; ids < 0 are empty slots.  Returns (ids [Q, k] padded -1, dists padded +inf)."""

@@ -148,3 +148,12 @@ def test_cpu_indexer_flow_matches_reference(oracle, golden):
     ids, ncand = idx.query(golden["l2_Q"], k=int(golden["l2_k"]))
     assert ncand == golden["l2_query_ncand"].tolist()
     assert ids == unpad(golden["l2_query_ids"])
+
+
+def test_oracle_nearest_exclude_positive_small_case(oracle):
+    # triplet.py:44-74 on a case small enough to check by hand: points on a line
+    v = torch.tensor([[0.0], [1.0], [2.1], [3.3], [10.0]])
+    pos = torch.tensor([[1], [0], [1], [2], [3]])
+    got = oracle.nearest_exclude_positive(v, "l2sq", pos).tolist()
+    # row 0: not itself, not 1 -> 2;  row 1: not 0 -> 2;  row 2: not 1 -> 3;  row 3: not 2 -> 1;  row 4: not 3 -> 2
+    assert got == [2, 2, 3, 1, 2]
