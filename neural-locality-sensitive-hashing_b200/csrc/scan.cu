@@ -1226,7 +1226,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
     NLSH_CUDA_TRY(nlsh_post_launch());
     int rc = nlsh_scan_tc_prepare(w.qn, w.pairs, w.pair_off + n_buckets, n_pairs, p, geom.d_pad, w.qs,
                                   w.qs_norm, w.tau_g, n_queries, probes, offsets, x_sorted, n_rows,
-                                  n_buckets, geom.d, k, metric, w.pair_off, st);
+                                  n_buckets, geom.d, k, metric, st);
     if (rc != NLSH_OK) return rc;
     TcScanArgs t{};
     t.xs = x_sorted;

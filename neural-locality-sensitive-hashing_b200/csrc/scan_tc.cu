@@ -408,21 +408,6 @@ __global__ void __launch_bounds__(kThreads, 1)
           mask |= (fmaf(ra, __uint_as_float(v1[j4 + 3]), rb) <= t1.w ? 1u : 0u) << (16 + j4 + 3);
         }
         if (!valid) mask = 0;
-        if (a.prefetch && mask != 0) {
-          // the re-rank warps re-read a surviving row a few tiles later (they are the slower stage):
-          // start pulling its lines into L1 now, so that their loads hit there instead of in L2
-          const char* rp = reinterpret_cast<const char*>(a.xs + (size_t)row * a.d_pad);
-          const char* re = rp + (size_t)a.d * sizeof(float);
-          if (a.prefetch == 1) {
-            for (const char* l = rp - (reinterpret_cast<uintptr_t>(rp) & 127u); l < re; l += 128)
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(l));
-          } else {  // 2: touch every 32-byte sector with a load whose result is never used
-            for (const char* l = rp - (reinterpret_cast<uintptr_t>(rp) & 31u); l < re; l += 32) {
-              unsigned sink;
-              asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(sink) : "l"(l));
-            }
-          }
-        }
         const unsigned sb = tcount % kSurvBufs, use = tcount / kSurvBufs;
         TIMED_WAIT(2, &surv_empty[sb], (use & 1u) ^ 1u);  // the re-rank warps are done with this buffer
         int* cn = cnt + sb * kRerankWarps;
@@ -589,7 +574,7 @@ __global__ void __launch_bounds__(256)
 // every (query, bucket) list starts empty and the first 128-row tile of each bucket survives the
 // filter whole.  The bound is inflated by a few ulps-of-the-sum because the re-rank sums the same
 // terms in a different order.
-constexpr int kMaxSeedRows = 512;
+constexpr int kMaxSeedRows = 256;
 
 template <int METRIC>
 __global__ void __launch_bounds__(128)
@@ -661,143 +646,6 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// The same seed, organised by BUCKET: the ~Q / B queries whose first probe is the same bucket read the
-// same sample rows, and one warp per query (above) fetches them once per query - 1.3 GB through L2
-// for the 10k-query batch of config 4, 0.22 ms, where the distinct sample rows are 0.54 GB.  Here a
-// warp owns (bucket, chunk of the bucket's pairs): it picks the chunk's first-probe pairs (flat probe
-// index f with f % p == 0) and scores up to kSeedM of their queries against every sample row it loads,
-// so a row is fetched about once per bucket.  The queries sit in shared memory (one float4 chunk per
-// lane and query), which leaves the registers for two row steps in flight (the first version kept
-// the queries in registers: 128 registers, 8 active warps per SM, latency bound, slower than the
-// per-query kernel).  Per query the arithmetic (8 lanes per row, four rows per step, columns in
-// ascending order, xor-shuffle sum) and therefore tau is the same as in seed_tau_kernel.
-constexpr int kSeedM = 4;
-constexpr int kSeedWarps = 4;
-
-__device__ __forceinline__ void seed_load_rows(float4 (&dst)[4], const float* __restrict__ xb, int r, int n,
-                                               int d_pad, int l8) {
-  const int nvec = d_pad >> 2;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = l8 + 8 * i;
-    dst[i] = (r < n && c < nvec) ? *reinterpret_cast<const float4*>(xb + (size_t)r * d_pad + 4 * c)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
-template <int METRIC>
-__device__ __forceinline__ void seed_pass(const int (&qi)[kSeedM], const float4* __restrict__ qs,
-                                          const float* __restrict__ xb, int n, int d, int d_pad, int k,
-                                          float* __restrict__ tau_g) {
-  const int lane = lane_id();
-  const int l8 = lane & 7, g = lane >> 3;
-  WarpTopK<1, int> top[kSeedM];
-#pragma unroll
-  for (int m = 0; m < kSeedM; ++m) top[m].init(NLSH_ID_SENTINEL);
-  float4 xv[4], xn[4];
-  seed_load_rows(xv, xb, g, n, d_pad, l8);
-  for (int base = 0; base < n; base += 4) {
-    const int r = base + g;
-    seed_load_rows(xn, xb, r + 4, n, d_pad, l8);  // the next step's rows are in flight during this step's math
-    float acc[kSeedM], xx = 0.f;
-#pragma unroll
-    for (int m = 0; m < kSeedM; ++m) acc[m] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = l8 + 8 * i;
-      const int col0 = 4 * c;
-      if (col0 < d) {
-        const float xa[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
-        if (METRIC != NLSH_METRIC_L2) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (col0 + e < d) xx = fmaf(xa[e], xa[e], xx);
-        }
-#pragma unroll
-        for (int m = 0; m < kSeedM; ++m) {
-          const float4 qq = qs[m * 32 + c];
-          const float qa[4] = {qq.x, qq.y, qq.z, qq.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (col0 + e < d) {
-              if (METRIC == NLSH_METRIC_L2) {
-                const float t = (qa[e] - xa[e]) + 1e-6f;
-                acc[m] = fmaf(t, t, acc[m]);
-              } else {
-                acc[m] = fmaf(qa[e], xa[e], acc[m]);
-              }
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-#pragma unroll
-      for (int m = 0; m < kSeedM; ++m) acc[m] += __shfl_xor_sync(NLSH_FULL_MASK, acc[m], o);
-      if (METRIC != NLSH_METRIC_L2) xx += __shfl_xor_sync(NLSH_FULL_MASK, xx, o);
-    }
-#pragma unroll
-    for (int m = 0; m < kSeedM; ++m) {
-      const float dist = METRIC == NLSH_METRIC_L2 ? acc[m] : 1.0f - acc[m] / fmaxf(sqrtf(xx), 1e-8f);
-      top[m].offer(dist, r, l8 == 0 && r < n && qi[m] >= 0, k);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) xv[i] = xn[i];
-  }
-#pragma unroll
-  for (int m = 0; m < kSeedM; ++m) {
-    if (lane == 0 && qi[m] >= 0 && top[m].tau < pos_inf()) {
-      const float t = top[m].tau;
-      tau_g[qi[m]] = METRIC == NLSH_METRIC_L2 ? t * 1.00002f + 1e-30f : t + 4e-6f + 2e-5f * fabsf(t);
-    }
-  }
-}
-
-template <int METRIC>
-__global__ void __launch_bounds__(32 * kSeedWarps, 4)
-    seed_tau_bucket_kernel(const float* __restrict__ qn, const int* __restrict__ pairs,
-                           const int* __restrict__ pair_off, const int* __restrict__ offsets,
-                           const float* __restrict__ xs, int n_buckets, int p, int d, int d_pad, int k,
-                           int seed_rows, int chunk, int cpb, float* __restrict__ tau_g) {
-  __shared__ float4 q_s[kSeedWarps][kSeedM * 32];  // per warp: chunk c of query m at [m * 32 + c]
-  const int wb = threadIdx.x >> 5;
-  const long long w = (long long)blockIdx.x * kSeedWarps + wb;
-  const long long bl = w / cpb;
-  if (bl >= n_buckets) return;
-  const int b = (int)bl, c = (int)(w - bl * cpb);
-  const int lane = lane_id();
-  const int nvec = d_pad >> 2;
-  const int r0 = offsets[b];
-  int n = offsets[b + 1] - r0;
-  if (n > seed_rows) n = seed_rows;
-  if (n < k) return;
-  const int p1 = pair_off[b + 1];
-  for (int base = pair_off[b] + c * chunk; base < p1; base += cpb * chunk) {  // warp-uniform
-    const int i = base + lane;
-    const int f = (lane < chunk && i < p1) ? pairs[i] : -1;
-    unsigned todo = __ballot_sync(NLSH_FULL_MASK, f >= 0 && f % p == 0);  // the pairs that are a query's first probe
-    while (todo) {
-      int qi[kSeedM];
-#pragma unroll
-      for (int m = 0; m < kSeedM; ++m) {
-        const int src = todo ? __ffs(todo) - 1 : 0;
-        const int fq = __shfl_sync(NLSH_FULL_MASK, f, src);
-        qi[m] = todo ? fq / p : -1;
-        todo &= todo - 1;  // 0 stays 0
-      }
-      __syncwarp();  // the previous pass has read its queries
-#pragma unroll
-      for (int m = 0; m < kSeedM; ++m)
-        q_s[wb][m * 32 + lane] = (qi[m] >= 0 && lane < nvec)
-                                     ? *reinterpret_cast<const float4*>(qn + (size_t)qi[m] * d_pad + 4 * lane)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-      __syncwarp();
-      seed_pass<METRIC>(qi, q_s[wb], xs + (size_t)r0 * d_pad, n, d, d_pad, k, tau_g);
-    }
-  }
-}
-
 size_t scan_tc_smem(int kblocks, int n_slots) {
   return (size_t)n_slots * kSlotBytes + (size_t)kMetaBufs * kMetaBytes + (size_t)kItemBufs * kblocks * kQBoxBytes +
          kSurvBufs * kRerankWarps * kListCap * sizeof(uint16_t) + 4 * kItemBufs * kTcNQ * sizeof(float) +
@@ -815,8 +663,7 @@ bool nlsh_scan_tc_supported(int d, int k, int metric) {
 int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, long long n_pairs,
                          int p, int d_pad, float* qs, float* qs_norm, float* tau_g,
                          long long n_queries, const int* probes, const int* offsets, const float* xs,
-                         long long n_rows, int n_buckets, int d, int k, int metric, const int* pair_off,
-                         cudaStream_t st) {
+                         long long n_rows, int n_buckets, int d, int k, int metric, cudaStream_t st) {
   long long threads = n_pairs * 32;
   if (threads < n_queries) threads = n_queries;
   long long blocks = (threads + 255) / 256;
@@ -838,27 +685,6 @@ int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, 
   if (const char* env = getenv("NLSH_SCAN_SEED")) seed_rows = atoi(env);
   if (seed_rows <= 0) return NLSH_OK;
   if (seed_rows > kMaxSeedRows) seed_rows = kMaxSeedRows;
-  const char* impl = getenv("NLSH_SEED_IMPL");  // "bucket" | "query"
-  if (impl != nullptr && strcmp(impl, "bucket") == 0 && pair_off != nullptr && n_buckets > 0) {
-    // a warp takes about four first-probe queries: 4 p pairs of its bucket (every p-th pair is one)
-    int chunk = 4 * p;
-    if (chunk > 32) chunk = 32;
-    if (chunk < 4) chunk = 4;
-    const long long avg_pairs = n_pairs / n_buckets;
-    long long cpb = (avg_pairs + chunk / 2) / chunk;  // warps per bucket; longer pair lists are walked in strides
-    if (cpb < 1) cpb = 1;
-    if (cpb > 64) cpb = 64;
-    const long long warps = (long long)n_buckets * cpb;
-    const unsigned gb = (unsigned)((warps + kSeedWarps - 1) / kSeedWarps);
-    if (metric == NLSH_METRIC_L2)
-      seed_tau_bucket_kernel<NLSH_METRIC_L2><<<gb, 32 * kSeedWarps, 0, st>>>(qn, pairs, pair_off, offsets, xs, n_buckets, p, d,
-                                                                d_pad, k, seed_rows, chunk, (int)cpb, tau_g);
-    else
-      seed_tau_bucket_kernel<NLSH_METRIC_ANGULAR><<<gb, 32 * kSeedWarps, 0, st>>>(qn, pairs, pair_off, offsets, xs, n_buckets,
-                                                                     p, d, d_pad, k, seed_rows, chunk, (int)cpb,
-                                                                     tau_g);
-    return nlsh_check_cuda(nlsh_post_launch(), "seed_tau_bucket_kernel launch");
-  }
   const unsigned sb = (unsigned)((n_queries + 3) / 4);
   if (metric == NLSH_METRIC_L2)
     seed_tau_kernel<NLSH_METRIC_L2><<<sb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad, k,
@@ -875,12 +701,7 @@ int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {
   int n_slots = kMaxSlots;
   // each K block's slot is freed by its own tcgen05.commit, so any ring depth >= 2 makes progress
   while (n_slots > 3 && scan_tc_smem(a.kblocks, n_slots) > 224 * 1024) --n_slots;
-  if (const char* env = getenv("NLSH_TC_SLOTS")) {  // A/B: a shallower ring leaves more of the SM's 256 KB to L1
-    const int cap = atoi(env);
-    if (cap >= 3 && cap < n_slots) n_slots = cap;
-  }
   a.n_slots = n_slots;
-  if (const char* env = getenv("NLSH_TC_PREFETCH")) a.prefetch = atoi(env);
   const size_t smem = scan_tc_smem(a.kblocks, n_slots);
   CUtensorMap map_x, map_q;
   int rc;

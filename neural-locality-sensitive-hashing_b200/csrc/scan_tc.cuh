@@ -33,7 +33,6 @@ struct TcScanArgs {
   long long n_rows;
   long long n_pairs;
   int p, k, d, d_pad, kblocks, max_chunks, n_slots;
-  int prefetch;          // filter threads pull the lines of a surviving row into L1 for the re-rank warps
   float l2_slack;        // 2.1e-6 * sqrt(d): bound of the eps cross term of F.pairwise_distance
 };
 
@@ -43,6 +42,5 @@ bool nlsh_scan_tc_supported(int d, int k, int metric);
 int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, long long n_pairs,
                          int p, int d_pad, float* qs, float* qs_norm, float* tau_g,
                          long long n_queries, const int* probes, const int* offsets, const float* xs,
-                         long long n_rows, int n_buckets, int d, int k, int metric, const int* pair_off,
-                         cudaStream_t st);
+                         long long n_rows, int n_buckets, int d, int k, int metric, cudaStream_t st);
 int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st);
