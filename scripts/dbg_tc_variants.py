@@ -24,7 +24,7 @@ Q = synth.make_queries(nq, d, hs, seed, dev, sep=bench.SEP)
 hashing, _ = bench.make_hashing(d, hs, metric, seed, dev, 300)
 idx = Indexer(hashing, X, hashing.distance, metric=metric)
 probes = idx.hash_tensors(Q, p)
-SWITCHES = ("NLSH_TC_PREFETCH", "NLSH_TC_SLOTS", "NLSH_SCAN_SEED", "NLSH_SEED_IMPL", "NLSH_TC_STATS")
+SWITCHES = ("NLSH_TC_PREFETCH", "NLSH_TC_SLOTS", "NLSH_SCAN_SEED", "NLSH_SEED_IMPL", "NLSH_SEED_ORDER", "NLSH_TC_STATS")
 VARIANTS = [{}] + [dict(kv.split("=") for kv in v.split(",")) for v in os.environ.get(
     "TC_VARIANTS", "NLSH_TC_PREFETCH=1;NLSH_TC_PREFETCH=2;NLSH_TC_SLOTS=6;NLSH_TC_SLOTS=5;"
     "NLSH_TC_PREFETCH=1,NLSH_TC_SLOTS=5;NLSH_TC_PREFETCH=2,NLSH_TC_SLOTS=5;"
