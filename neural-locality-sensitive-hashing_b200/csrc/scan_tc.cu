@@ -574,14 +574,15 @@ __global__ void __launch_bounds__(256)
 // every (query, bucket) list starts empty and the first 128-row tile of each bucket survives the
 // filter whole.  The bound is inflated by a few ulps-of-the-sum because the re-rank sums the same
 // terms in a different order.
-constexpr int kMaxSeedRows = 512;
-constexpr bool kSeedByBucketDefault = false;  // see nlsh_scan_tc_prepare
+constexpr int kMaxSeedRows = 256;
 
 template <int METRIC>
-__device__ __forceinline__ void seed_query(long long q, const float* __restrict__ qn,
-                                           const int* __restrict__ probes, const int* __restrict__ offsets,
-                                           const float* __restrict__ xs, int n_buckets, int p, int d, int d_pad,
-                                           int k, int seed_rows, float* __restrict__ tau_g) {
+__global__ void __launch_bounds__(128)
+    seed_tau_kernel(const float* __restrict__ qn, const int* __restrict__ probes,
+                    const int* __restrict__ offsets, const float* __restrict__ xs, int n_buckets, int p,
+                    int d, int d_pad, int k, int seed_rows, long long n_queries, float* __restrict__ tau_g) {
+  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n_queries) return;
   const int lane = lane_id();
   const int b = probes[q * p];
   if (b < 0 || b >= n_buckets) return;
@@ -645,48 +646,6 @@ __device__ __forceinline__ void seed_query(long long q, const float* __restrict_
   }
 }
 
-// One warp per query, queries in input order.
-template <int METRIC>
-__global__ void __launch_bounds__(128)
-    seed_tau_kernel(const float* __restrict__ qn, const int* __restrict__ probes,
-                    const int* __restrict__ offsets, const float* __restrict__ xs, int n_buckets, int p,
-                    int d, int d_pad, int k, int seed_rows, long long n_queries, float* __restrict__ tau_g) {
-  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (q >= n_queries) return;
-  seed_query<METRIC>(q, qn, probes, offsets, xs, n_buckets, p, d, d_pad, k, seed_rows, tau_g);
-}
-
-// The same work with the queries taken in BUCKET order: `pairs` lists the (query, probe) pairs grouped
-// by bucket, and the pairs with f % p == 0 are the queries' first probes.  A block takes a window of
-// consecutive pairs (4 p of them, about four first probes) and deals its first-probe queries to its
-// four warps, so the warps of a block mostly sample the SAME bucket at the same time and the second
-// to fourth reader of a row hit L1 / merge with the miss in flight instead of going to L2 again (in
-// input order the ~Q / B queries of a bucket are spread over the grid: 1.3 GB through L2 for the
-// 10k-query batch of config 4, of which 0.54 GB are distinct rows).  Per query nothing changes.
-template <int METRIC>
-__global__ void __launch_bounds__(128)
-    seed_tau_sorted_kernel(const float* __restrict__ qn, const int* __restrict__ probes,
-                           const int* __restrict__ offsets, const float* __restrict__ xs, int n_buckets,
-                           int p, int d, int d_pad, int k, int seed_rows, const int* __restrict__ pairs,
-                           const int* __restrict__ n_valid, long long n_pairs, int window,
-                           float* __restrict__ tau_g) {
-  const int lane = lane_id();
-  const int w = threadIdx.x >> 5;
-  long long nv = *n_valid;
-  if (nv > n_pairs) nv = n_pairs;
-  const long long i = (long long)blockIdx.x * window + lane;
-  const int f = (lane < window && i < nv) ? pairs[i] : -1;
-  unsigned todo = __ballot_sync(NLSH_FULL_MASK, f >= 0 && f % p == 0);
-  for (int j = 0; todo != 0; ++j) {  // warp-uniform
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    if ((j & 3) == w) {
-      const int fq = __shfl_sync(NLSH_FULL_MASK, f, src);
-      seed_query<METRIC>(fq / p, qn, probes, offsets, xs, n_buckets, p, d, d_pad, k, seed_rows, tau_g);
-    }
-  }
-}
-
 size_t scan_tc_smem(int kblocks, int n_slots) {
   return (size_t)n_slots * kSlotBytes + (size_t)kMetaBufs * kMetaBytes + (size_t)kItemBufs * kblocks * kQBoxBytes +
          kSurvBufs * kRerankWarps * kListCap * sizeof(uint16_t) + 4 * kItemBufs * kTcNQ * sizeof(float) +
@@ -726,22 +685,6 @@ int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, 
   if (const char* env = getenv("NLSH_SCAN_SEED")) seed_rows = atoi(env);
   if (seed_rows <= 0) return NLSH_OK;
   if (seed_rows > kMaxSeedRows) seed_rows = kMaxSeedRows;
-  // NLSH_SEED_ORDER=input|bucket: which query each warp takes (A/B; results do not depend on it)
-  const char* order = getenv("NLSH_SEED_ORDER");
-  const bool by_bucket = order != nullptr ? strcmp(order, "bucket") == 0 : kSeedByBucketDefault;
-  if (by_bucket && n_pairs > 0) {
-    int window = 4 * p;
-    if (window > 32) window = 32;
-    const unsigned wb = (unsigned)((n_pairs + window - 1) / window);
-    if (metric == NLSH_METRIC_L2)
-      seed_tau_sorted_kernel<NLSH_METRIC_L2><<<wb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad, k,
-                                                                seed_rows, pairs, n_valid, n_pairs, window, tau_g);
-    else
-      seed_tau_sorted_kernel<NLSH_METRIC_ANGULAR><<<wb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d,
-                                                                     d_pad, k, seed_rows, pairs, n_valid, n_pairs,
-                                                                     window, tau_g);
-    return nlsh_check_cuda(nlsh_post_launch(), "seed_tau_sorted_kernel launch");
-  }
   const unsigned sb = (unsigned)((n_queries + 3) / 4);
   if (metric == NLSH_METRIC_L2)
     seed_tau_kernel<NLSH_METRIC_L2><<<sb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad, k,

@@ -5,8 +5,8 @@ whole-call ms, survivor / wait counters (NLSH_TC_STATS), and torch.equal against
     python scripts/dbg_tc_variants.py [workload] [p] [rows]
 
 NLSH_SCAN_SEED (seed sample rows) is a switch of the shipped library; NLSH_TC_PREFETCH, NLSH_TC_SLOTS and
-NLSH_SEED_IMPL were experiments of round 1 that lost and exist only at commit
-3b86946 - with the current library they are ignored.  TC_VARIANTS="A=1,B=2;C=3" sets the list.
+NLSH_SEED_IMPL (commit 3b86946) and NLSH_SEED_ORDER (the commit after it) were experiments of round 1 that
+lost - with the current library they are ignored.  TC_VARIANTS="A=1,B=2;C=3" sets the list.
 """
 import os, sys, json, torch
 sys.path.insert(0, "neural-locality-sensitive-hashing_b200"); sys.path.insert(0, ".")
