@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(256)
 // every (query, bucket) list starts empty and the first 128-row tile of each bucket survives the
 // filter whole.  The bound is inflated by a few ulps-of-the-sum because the re-rank sums the same
 // terms in a different order.
-constexpr int kMaxSeedRows = 256;
+constexpr int kMaxSeedRows = 512;
 
 template <int METRIC>
 __global__ void __launch_bounds__(128)
@@ -646,6 +646,107 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// The same seed with three row steps in flight per warp.  seed_tau_kernel has one: a step is four
+// 16-byte loads per lane, then the math that needs them, so a warp spends each of its 64 steps (256
+// sample rows) waiting out a full memory latency - measured 0.25 ms for the 10k-query batch of
+// config 4, about 1.3 us per step with 32 warps per SM.  Here the query sits in shared memory (one
+// float4 chunk per lane), which frees the registers for a ring of three row buffers: the loads of
+// steps i + 1 and i + 2 are in flight while step i is scored.  Per query the arithmetic (8 lanes per
+// row, four rows per step, columns in ascending order, xor-shuffle sum, offers in row order) and
+// therefore tau is the same as in seed_tau_kernel.
+__device__ __forceinline__ void seed_load_rows(float4 (&dst)[4], const float* __restrict__ xb, int r, int n,
+                                               int d_pad, int l8) {
+  const int nvec = d_pad >> 2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = l8 + 8 * i;
+    dst[i] = (r < n && c < nvec) ? *reinterpret_cast<const float4*>(xb + (size_t)r * d_pad + 4 * c)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int METRIC>
+__device__ __forceinline__ void seed_step(const float4 (&xv)[4], const float4* __restrict__ qs, int r, int n,
+                                          int d, int l8, int k, WarpTopK<1, int>& top) {
+  float acc = 0.f, xx = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = l8 + 8 * i;
+    const int col0 = 4 * c;
+    if (col0 < d) {
+      const float4 qq = qs[c];
+      const float xa[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+      const float qa[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (col0 + e < d) {
+          if (METRIC == NLSH_METRIC_L2) {
+            const float t = (qa[e] - xa[e]) + 1e-6f;
+            acc = fmaf(t, t, acc);
+          } else {
+            acc = fmaf(qa[e], xa[e], acc);
+            xx = fmaf(xa[e], xa[e], xx);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    acc += __shfl_xor_sync(NLSH_FULL_MASK, acc, o);
+    if (METRIC != NLSH_METRIC_L2) xx += __shfl_xor_sync(NLSH_FULL_MASK, xx, o);
+  }
+  const float dist = METRIC == NLSH_METRIC_L2 ? acc : 1.0f - acc / fmaxf(sqrtf(xx), 1e-8f);
+  top.offer(dist, r, l8 == 0 && r < n, k);
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(128, 6)
+    seed_tau_pipe_kernel(const float* __restrict__ qn, const int* __restrict__ probes,
+                         const int* __restrict__ offsets, const float* __restrict__ xs, int n_buckets, int p,
+                         int d, int d_pad, int k, int seed_rows, long long n_queries,
+                         float* __restrict__ tau_g) {
+  __shared__ float4 q_s[4][32];  // per warp: 16-byte chunk c of its query at [c]
+  const int wb = threadIdx.x >> 5;
+  const long long q = (long long)blockIdx.x * 4 + wb;
+  if (q >= n_queries) return;
+  const int lane = lane_id();
+  const int b = probes[q * p];
+  if (b < 0 || b >= n_buckets) return;
+  const int r0 = offsets[b];
+  int n = offsets[b + 1] - r0;
+  if (n > seed_rows) n = seed_rows;
+  if (n < k) return;
+  const int l8 = lane & 7, g = lane >> 3;
+  q_s[wb][lane] = lane < (d_pad >> 2) ? *reinterpret_cast<const float4*>(qn + q * d_pad + 4 * lane)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  const float* xb = xs + (size_t)r0 * d_pad;
+  const float4* qs = q_s[wb];
+  float4 x0[4], x1[4], x2[4];
+  seed_load_rows(x0, xb, g, n, d_pad, l8);
+  seed_load_rows(x1, xb, 4 + g, n, d_pad, l8);
+  seed_load_rows(x2, xb, 8 + g, n, d_pad, l8);
+  WarpTopK<1, int> top;
+  top.init(NLSH_ID_SENTINEL);
+  for (int base = 0; base < n; base += 12) {  // warp-uniform
+    seed_step<METRIC>(x0, qs, base + g, n, d, l8, k, top);
+    seed_load_rows(x0, xb, base + 12 + g, n, d_pad, l8);
+    if (base + 4 < n) {
+      seed_step<METRIC>(x1, qs, base + 4 + g, n, d, l8, k, top);
+      seed_load_rows(x1, xb, base + 16 + g, n, d_pad, l8);
+    }
+    if (base + 8 < n) {
+      seed_step<METRIC>(x2, qs, base + 8 + g, n, d, l8, k, top);
+      seed_load_rows(x2, xb, base + 20 + g, n, d_pad, l8);
+    }
+  }
+  if (lane == 0 && top.tau < pos_inf()) {
+    const float t = top.tau;
+    tau_g[q] = METRIC == NLSH_METRIC_L2 ? t * 1.00002f + 1e-30f : t + 4e-6f + 2e-5f * fabsf(t);
+  }
+}
+
 size_t scan_tc_smem(int kblocks, int n_slots) {
   return (size_t)n_slots * kSlotBytes + (size_t)kMetaBufs * kMetaBytes + (size_t)kItemBufs * kblocks * kQBoxBytes +
          kSurvBufs * kRerankWarps * kListCap * sizeof(uint16_t) + 4 * kItemBufs * kTcNQ * sizeof(float) +
@@ -675,17 +776,33 @@ int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, 
   gather_pair_queries_kernel<<<(unsigned)blocks, 256, 0, st>>>(qn, pairs, n_valid, n_pairs, p, d_pad, qs,
                                                              qs_norm, tau_g, n_queries);
   NLSH_CUDA_TRY(nlsh_post_launch());
-  // rows sampled per bucket: half of the average bucket, between 32 and 128 (256 for big buckets)
+  // rows sampled per bucket: half of the average bucket, between 32 and 128; more for larger buckets,
+  // where a sample step costs the seed kernel less than it saves the scan (measured with the pipelined
+  // seed kernel, 10k queries, p = 8: 305-row buckets 128 -> 192 rows: step 0.586 -> 0.551 ms, 256 rows
+  // the same; 2441-row buckets 256 -> 384 rows: 1.688 -> 1.654 ms, 512 rows no further gain)
   // (NLSH_SCAN_SEED=<rows> overrides; 0 = no seeding, for A/B runs)
   const long long avg = n_buckets > 0 ? n_rows / n_buckets : 0;
   int seed_rows = (int)(avg / 2 / 32 * 32);
   if (seed_rows < 32) seed_rows = 32;
   if (seed_rows > 128) seed_rows = 128;
-  if (avg >= 2048) seed_rows = 256;  // big buckets: the tighter start pays for the larger sample (measured)
+  if (avg >= 256) seed_rows = 192;
+  if (avg >= 1024) seed_rows = 256;
+  if (avg >= 2048) seed_rows = 384;
   if (const char* env = getenv("NLSH_SCAN_SEED")) seed_rows = atoi(env);
   if (seed_rows <= 0) return NLSH_OK;
   if (seed_rows > kMaxSeedRows) seed_rows = kMaxSeedRows;
   const unsigned sb = (unsigned)((n_queries + 3) / 4);
+  // NLSH_SEED_PIPE=0: the one-step-in-flight kernel (A/B; tau does not depend on the choice)
+  const char* pipe = getenv("NLSH_SEED_PIPE");
+  if (pipe == nullptr || atoi(pipe) != 0) {
+    if (metric == NLSH_METRIC_L2)
+      seed_tau_pipe_kernel<NLSH_METRIC_L2><<<sb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad, k,
+                                                              seed_rows, n_queries, tau_g);
+    else
+      seed_tau_pipe_kernel<NLSH_METRIC_ANGULAR><<<sb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad,
+                                                                   k, seed_rows, n_queries, tau_g);
+    return nlsh_check_cuda(nlsh_post_launch(), "seed_tau_pipe_kernel launch");
+  }
   if (metric == NLSH_METRIC_L2)
     seed_tau_kernel<NLSH_METRIC_L2><<<sb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad, k,
                                                        seed_rows, n_queries, tau_g);

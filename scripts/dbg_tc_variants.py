@@ -4,7 +4,8 @@ whole-call ms, survivor / wait counters (NLSH_TC_STATS), and torch.equal against
 
     python scripts/dbg_tc_variants.py [workload] [p] [rows]
 
-NLSH_SCAN_SEED (seed sample rows) is a switch of the shipped library; NLSH_TC_PREFETCH, NLSH_TC_SLOTS and
+NLSH_SCAN_SEED (seed sample rows) and NLSH_SEED_PIPE (0 = the one-step-in-flight seed kernel) are switches
+of the shipped library; NLSH_TC_PREFETCH, NLSH_TC_SLOTS and
 NLSH_SEED_IMPL (commit 3b86946) and NLSH_SEED_ORDER (the commit after it) were experiments of round 1 that
 lost - with the current library they are ignored.  TC_VARIANTS="A=1,B=2;C=3" sets the list.
 """
@@ -24,7 +25,7 @@ Q = synth.make_queries(nq, d, hs, seed, dev, sep=bench.SEP)
 hashing, _ = bench.make_hashing(d, hs, metric, seed, dev, 300)
 idx = Indexer(hashing, X, hashing.distance, metric=metric)
 probes = idx.hash_tensors(Q, p)
-SWITCHES = ("NLSH_TC_PREFETCH", "NLSH_TC_SLOTS", "NLSH_SCAN_SEED", "NLSH_SEED_IMPL", "NLSH_SEED_ORDER", "NLSH_TC_STATS")
+SWITCHES = ("NLSH_TC_PREFETCH", "NLSH_TC_SLOTS", "NLSH_SCAN_SEED", "NLSH_SEED_IMPL", "NLSH_SEED_ORDER", "NLSH_SEED_PIPE", "NLSH_TC_STATS")
 VARIANTS = [{}] + [dict(kv.split("=") for kv in v.split(",")) for v in os.environ.get(
     "TC_VARIANTS", "NLSH_TC_PREFETCH=1;NLSH_TC_PREFETCH=2;NLSH_TC_SLOTS=6;NLSH_TC_SLOTS=5;"
     "NLSH_TC_PREFETCH=1,NLSH_TC_SLOTS=5;NLSH_TC_PREFETCH=2,NLSH_TC_SLOTS=5;"
