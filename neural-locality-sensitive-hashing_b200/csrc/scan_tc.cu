@@ -568,8 +568,10 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Initial tau_g: the exact k-th best distance of each query among the first rows (128 by default) of its
-// first probed bucket (one warp per query, one or two rows per lane).  Any k candidates bound the
+// Initial tau_g: the exact k-th best distance of each query among the first rows (32 to 384, by bucket
+// size, see nlsh_scan_tc_prepare) of its first probed bucket (one warp per query, 8 lanes per row, four
+// rows per step).  This is the one-step-in-flight version, kept for A/B (NLSH_SEED_PIPE=0); the
+// library runs seed_tau_pipe_kernel below.  Any k candidates bound the
 // final k-th distance from above, so this is a valid threshold from the very first tile; without it
 // every (query, bucket) list starts empty and the first 128-row tile of each bucket survives the
 // filter whole.  The bound is inflated by a few ulps-of-the-sum because the re-rank sums the same
