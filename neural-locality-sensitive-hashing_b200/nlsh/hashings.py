@@ -41,38 +41,53 @@ def _fold_batchnorm(weight, bias, bn):
     return w, b
 
 
-def extract_layer_tensors(encoder, output_layer):
-    """Read the live weights of `encoder` (+ `output_layer`) as [(weight, bias, act), ...].
+def _leaf_modules(module):
+    """Leaf modules of `module` in definition order (containers such as nn.Sequential or the SIREN
+    wrapper of encoders.py:72-76 are walked, not returned)."""
+    for child in module.children():
+        if next(child.children(), None) is None:
+            yield child
+        else:
+            yield from _leaf_modules(child)
 
-    Supported trunks: any nn.Sequential-like module whose children are nn.Linear, nn.ReLU,
-    nn.Identity, nn.Dropout (eval) or eval-mode nn.BatchNorm1d (encoders.py:24-55), and
-    modules exposing fc1/fc2 Linear attributes applied with ReLU (encoders.py:8-21).
-    Weights are re-read at every call because they change between index builds while
-    training (base.py:80-86).
+
+def extract_layer_specs(encoder, output_layer):
+    """Read the live weights of `encoder` (+ `output_layer`) as [(weight, bias, act, act_scale), ...].
+
+    Supported trunks: any nn.Sequential-like module whose leaves are nn.Linear, nn.ReLU, a `Sine`
+    (sin(w0 x), the SIREN trunk of encoders.py:58-79), nn.Identity, nn.Dropout (eval) or eval-mode
+    nn.BatchNorm1d (encoders.py:24-55), and modules exposing fc1/fc2 Linear attributes applied
+    with ReLU (encoders.py:8-21).  Weights are re-read at every call because they change between
+    index builds while training (base.py:80-86).
     """
-    pending = []  # [weight, bias, act]
+    pending = []  # [weight, bias, act, act_scale]
 
     def add_linear(lin):
         pending.append([lin.weight.detach(), lin.bias.detach() if lin.bias is not None else None,
-                        _native.ACT_IDENTITY])
+                        _native.ACT_IDENTITY, 1.0])
 
     if hasattr(encoder, "fc1") and hasattr(encoder, "fc2") and isinstance(encoder.fc1, nn.Linear):
         for lin in (encoder.fc1, encoder.fc2):
             add_linear(lin)
             pending[-1][2] = _native.ACT_RELU
     else:
-        children = list(encoder.children()) if isinstance(encoder, nn.Module) else None
-        if not children:
+        leaves = list(_leaf_modules(encoder)) if isinstance(encoder, nn.Module) else None
+        if not leaves:
             raise NotImplementedError(
                 f"encoder {type(encoder).__name__} is not a Linear/ReLU stack; the B200 hasher "
                 "kernel has no PyTorch fallback")
-        for child in children:
+        for child in leaves:
             if isinstance(child, nn.Linear):
                 add_linear(child)
             elif isinstance(child, nn.ReLU):
                 if not pending or pending[-1][2] != _native.ACT_IDENTITY:
                     raise NotImplementedError("ReLU without a preceding Linear")
                 pending[-1][2] = _native.ACT_RELU
+            elif type(child).__name__ == "Sine" and hasattr(child, "w0"):
+                if not pending or pending[-1][2] != _native.ACT_IDENTITY:
+                    raise NotImplementedError("Sine without a preceding Linear")
+                pending[-1][2] = _native.ACT_SIN
+                pending[-1][3] = float(child.w0)
             elif isinstance(child, nn.BatchNorm1d):
                 if not pending or pending[-1][2] != _native.ACT_IDENTITY:
                     raise NotImplementedError("BatchNorm1d must directly follow a Linear")
@@ -82,14 +97,23 @@ def extract_layer_tensors(encoder, output_layer):
             else:
                 raise NotImplementedError(
                     f"encoder child {type(child).__name__} is not supported by the B200 hasher "
-                    "kernel (Linear / ReLU / eval BatchNorm1d only; no PyTorch fallback)")
+                    "kernel (Linear / ReLU / Sine / eval BatchNorm1d only; no PyTorch fallback)")
     add_linear(output_layer)
     return [tuple(entry) for entry in pending]
 
 
+def extract_layer_tensors(encoder, output_layer):
+    """extract_layer_specs without the activation scale: [(weight, bias, act), ...] for the ReLU trunks
+    (the callers that unpack three fields); a Sine layer needs its w0, so it is refused here."""
+    specs = extract_layer_specs(encoder, output_layer)
+    if any(act == _native.ACT_SIN for _, _, act, _ in specs):
+        raise NotImplementedError("sine layers carry a scale: use extract_layer_specs")
+    return [(w, b, act) for w, b, act, _ in specs]
+
+
 def extract_layers(encoder, output_layer):
-    """extract_layer_tensors as CUDA LayerSpecs for the C ABI."""
-    return [_native.LayerSpec(w, b, act) for w, b, act in extract_layer_tensors(encoder, output_layer)]
+    """extract_layer_specs as CUDA LayerSpecs for the C ABI."""
+    return [_native.LayerSpec(w, b, act, scale) for w, b, act, scale in extract_layer_specs(encoder, output_layer)]
 
 
 def codes_to_sets(probes) -> List[Set[int]]:

@@ -69,12 +69,14 @@ def hash_codes_c(codes) -> List[Set[int]]:
 # encoders.py + nlsh/hashings.py
 # ---------------------------------------------------------------------------------------
 class Layer:
-    """weight [out, in], bias [out] | None (torch CPU fp32), relu flag."""
+    """weight [out, in], bias [out] | None (torch CPU fp32), relu flag; sin_w0 = w0 of a SIREN sine
+    layer (encoders.py:58-79 through the third-party siren-torch: sin(w0 * x)), None otherwise."""
 
-    def __init__(self, weight, bias, relu):
+    def __init__(self, weight, bias, relu, sin_w0=None):
         self.weight = torch.as_tensor(weight, dtype=torch.float32)
         self.bias = None if bias is None else torch.as_tensor(bias, dtype=torch.float32)
         self.relu = bool(relu)
+        self.sin_w0 = None if sin_w0 is None else float(sin_w0)
 
 
 def mlp_logits(x, layers: Sequence[Layer]) -> torch.Tensor:
@@ -86,6 +88,8 @@ def mlp_logits(x, layers: Sequence[Layer]) -> torch.Tensor:
             h = F.linear(h, L.weight, L.bias)
             if L.relu:
                 h = F.relu(h)
+            if L.sin_w0 is not None:
+                h = torch.sin(L.sin_w0 * h)
     return h
 
 

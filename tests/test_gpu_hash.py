@@ -109,3 +109,30 @@ def test_empty_and_error_paths():
         h.hash(torch.zeros((2, 9)).cuda())
     with pytest.raises(_native.NativeLibraryError):
         h.hash(torch.zeros((2, 8)))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("NLSH_TEST_SIREN") != "1",
+                    reason="sine trunk (encoders.py:58-79): host side pinned on the CPU, the CUDA forward with "
+                           "NLSH_ACT_SIN has not been run on a GPU yet (round 1's GPU budget ended first); "
+                           "NLSH_TEST_SIREN=1 runs it")
+def test_siren_trunk_logits_against_oracle(oracle):
+    """Hasher forward over the SIREN trunk main.py:388 builds.  sin(30 x) amplifies the rounding of the
+    first layer 30-fold, so the bar is 1e-4 of the row scale, not the 1e-5 of the ReLU trunks; codes
+    must still follow bit-exactly from the device's own logits."""
+    from encoders import Siren
+    from nlsh import _native
+    from nlsh.hashings import MultivariateBernoulli, extract_layer_specs
+    torch.manual_seed(2)
+    hashing = MultivariateBernoulli(Siren(128, [256, 256, 64]), 12, None)
+    hashing.train_mode(False)
+    X = torch.randn(3000, 128) * 0.05
+    codes, _, logits = hashing.hash_tensors(X.cuda(), 1, want_logits=True)
+    hasher = hashing._hasher
+    layers = [oracle.Layer(w.cpu(), None if b is None else b.cpu(), act == _native.ACT_RELU,
+                           scale if act == _native.ACT_SIN else None)
+              for w, b, act, scale in extract_layer_specs(hasher._encoder, hasher.output_layer)]
+    ref = oracle.mlp_logits(X, layers).numpy()
+    got = logits.cpu().numpy()
+    scale = np.maximum(np.abs(ref), np.abs(ref).max(axis=1, keepdims=True))
+    assert (np.abs(got - ref) <= 1e-4 * scale).all()
+    assert np.array_equal(oracle.hard_codes(logits.cpu(), oracle.HEAD_SIGMOID), codes.cpu().numpy())

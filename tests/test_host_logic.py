@@ -55,6 +55,32 @@ def test_extract_layer_tensors_matches_module_forward(oracle):
         torch.testing.assert_close(oracle.mlp_logits(x, layers), want, rtol=1e-5, atol=1e-5)
 
 
+def test_siren_trunk_extraction_matches_module_forward(oracle):
+    """encoders.py:58-79 (the trunk main.py:388 builds): Linear -> sin(30 x), Linear -> sin(x), Linear,
+    then the hasher's output Linear; the extracted (weight, bias, act, w0) stack must reproduce the
+    module's forward.  The sine trunk comes from an unpinned third-party package: parity unpinned."""
+    from encoders import MultiLayerRelu, Siren  # noqa: F401 - main.py:9 imports exactly these two names
+    from nlsh import _native
+    from nlsh.hashings import MultivariateBernoulli, extract_layer_specs, extract_layer_tensors
+    torch.manual_seed(1)
+    enc = Siren(12, [16, 16, 8])
+    assert enc.output_dim == 8
+    hashing = MultivariateBernoulli(enc, 5, None)
+    hasher = hashing._hasher.cpu()
+    specs = extract_layer_specs(hasher._encoder, hasher.output_layer)
+    assert [(tuple(w.shape), act, scale) for w, _, act, scale in specs] == [
+        ((16, 12), _native.ACT_SIN, 30.0), ((16, 16), _native.ACT_SIN, 1.0),
+        ((8, 16), _native.ACT_IDENTITY, 1.0), ((5, 8), _native.ACT_IDENTITY, 1.0)]
+    layers = [oracle.Layer(w, b, act == _native.ACT_RELU, scale if act == _native.ACT_SIN else None)
+              for w, b, act, scale in specs]
+    x = torch.randn(17, 12) * 0.1
+    with torch.no_grad():
+        want = hasher.output_layer(hasher._encoder(x))
+    torch.testing.assert_close(oracle.mlp_logits(x, layers), want, rtol=1e-5, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        extract_layer_tensors(hasher._encoder, hasher.output_layer)  # three-field form has no room for w0
+
+
 def test_extract_layers_refuses_unknown_modules():
     from nlsh.hashings import extract_layer_tensors
     enc = nn.Sequential(nn.Linear(4, 4), nn.GELU())
