@@ -1,9 +1,15 @@
 """Host-side logic of the drop-in package that needs no GPU."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "neural-locality-sensitive-hashing_b200")
 
 
 def test_resolve_metric():
@@ -175,3 +181,30 @@ def test_vecs_round_trip(tmp_path):
     (tmp_path / "bad.fvecs").write_bytes(b"\x03\x00\x00\x00abc")
     with pytest.raises(ValueError):
         read_vecs(str(tmp_path / "bad.fvecs"))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/nlsh"), reason="needs a checkout of the reference")
+def test_overlay_on_the_reference_checkout():
+    """NLSH_REFERENCE_PATH: the reference's training glue (nlsh.trainers, nlsh.learning) imports on top
+    of this package and its Trainer picks up THIS package's Indexer / calculate_recall
+    (nlsh/trainers/base.py:7-8), which is the drop-in claim of INTEGRATION.md section 1."""
+    code = r"""
+import os, sys, types
+sys.modules["hnswlib"] = types.ModuleType("hnswlib")          # nlsh/trainers/hnsw.py:7, not installed here
+import nlsh, nlsh.indexer, nlsh.metrics, nlsh.hashings, nlsh.utils
+pkg = os.path.dirname(nlsh.__file__)
+import nlsh.learning.distances as dist                          # the reference's own file
+import nlsh.trainers.base as base                               # the reference's own file ...
+assert dist.__file__.startswith(os.environ["NLSH_REFERENCE_PATH"])
+assert base.__file__.startswith(os.environ["NLSH_REFERENCE_PATH"])
+assert base.Indexer is nlsh.indexer.Indexer                     # ... bound to this package's hot path
+assert base.calculate_recall is nlsh.metrics.calculate_recall
+for m in (nlsh.indexer, nlsh.metrics, nlsh.hashings, nlsh.utils):
+    assert os.path.dirname(m.__file__) == pkg, m.__file__
+from encoders import MultiLayerRelu, Siren                      # main.py:9
+print("overlay ok")
+"""
+    env = dict(os.environ, NLSH_REFERENCE_PATH="/root/reference",
+               PYTHONPATH=os.pathsep.join([PKG, os.environ.get("PYTHONPATH", "")]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "overlay ok" in out.stdout, out.stderr[-2000:]
