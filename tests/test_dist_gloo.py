@@ -44,6 +44,19 @@ def _worker(rank, world, port, out_dir):
         full_ids, full_d = oracle.knn_queries(Q, X, "l2", k)
         assert np.array_equal(m_ids, full_ids)
         np.testing.assert_allclose(m_d, full_d, rtol=1e-6)
+        # the packed exchange ShardedIndexer uses: ids | dists | n_cand of a rank in ONE byte buffer, one
+        # all-gather, strided [G, Q, k] views over the gathered bytes (the merge kernel reads them in place)
+        from nlsh.parallel import PackedLists
+        packed = PackedLists(Q.shape[0], k, world, torch.device("cpu"))
+        p_ids, p_d, p_n = packed.out()
+        p_ids.copy_(ids)
+        p_d.copy_(torch.from_numpy(dd))
+        p_n.fill_(hi - lo)
+        dist.all_gather_into_tensor(packed.gathered, packed.local)
+        assert torch.equal(packed.g_ids, g_ids) and torch.equal(packed.g_dists, g_d)
+        assert packed.g_ncand.sum(0).tolist() == [X.shape[0]] * Q.shape[0]
+        m2_ids, _ = oracle.merge_topk(packed.g_dists.numpy(), packed.g_ids.numpy(), k)
+        assert np.array_equal(m2_ids, full_ids)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
