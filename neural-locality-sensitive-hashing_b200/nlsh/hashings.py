@@ -122,6 +122,34 @@ def codes_to_sets(probes) -> List[Set[int]]:
     return [set(c for c in row if c >= 0) for row in rows]
 
 
+def _trunk_from_state_dict(sd):
+    """Rebuild the encoder module of a saved hasher from its state dict: the `{i}_linear` /
+    `{i}_batch_norm` naming of encoders.py:41-48 or the fc1 / fc2 pair of encoders.py:8-21."""
+    import re
+
+    from encoders import MultiLayerRelu, TwoLayer256Relu  # top-level module of this package's root
+    if "_encoder.fc1.weight" in sd:
+        return TwoLayer256Relu(sd["_encoder.fc1.weight"].shape[1], with_bias="_encoder.fc1.bias" in sd)
+    idx = sorted(int(m.group(1)) for m in (re.fullmatch(r"_encoder\.(\d+)_linear\.weight", k) for k in sd) if m)
+    if not idx or idx != list(range(len(idx))):
+        raise NotImplementedError(
+            "saved hasher is not a MultiLayerRelu / TwoLayer256Relu trunk (encoders.py:8-55); "
+            "construct the hashing yourself and load_state_dict into hashing._hasher")
+    weights = [sd[f"_encoder.{i}_linear.weight"] for i in idx]
+    return MultiLayerRelu(weights[0].shape[1], [w.shape[0] for w in weights],
+                          with_batchnorm=any("_batch_norm." in k for k in sd),
+                          with_bias="_encoder.0_linear.bias" in sd)
+
+
+def _load_scripted(cls, path, distance_func, kwargs):
+    scripted = torch.jit.load(path, map_location="cpu")
+    sd = {k: v.detach().clone() for k, v in scripted.state_dict().items()}
+    hashing = cls(_trunk_from_state_dict(sd), sd["output_layer.weight"].shape[0], distance_func, **kwargs(scripted))
+    hashing._hasher.load_state_dict(sd)
+    hashing.train_mode(False)
+    return hashing
+
+
 class MultivariateBernoulli:
 
     class _Hasher(nn.Module):
@@ -168,6 +196,14 @@ class MultivariateBernoulli:
         torch.jit.save(scripted_model_cpu, base_name + "_cpu.pt")
         scripted_model_gpu = torch.jit.script(self._hasher.cuda())
         torch.jit.save(scripted_model_gpu, base_name + "_gpu.pt")
+
+    @classmethod
+    def load(cls, path, distance_func):
+        """The `load` classmethod hashings.py:58 leaves as a TODO: rebuild the hashing (in eval mode)
+        from a TorchScript file written by `save` (base_name + "_cpu.pt" / "_gpu.pt", hashings.py:53-57;
+        eval.py:113 loads the same file), so that an index can be built from a stored model."""
+        return _load_scripted(cls, path, distance_func,
+                              kwargs=lambda m: {"tanh_output": bool(getattr(m, "_tanh_output", False))})
 
     def train_mode(self, on):
         if on:
@@ -250,6 +286,11 @@ class Categorical:
         torch.jit.save(scripted_model_cpu, base_name + "_cpu.pt")
         scripted_model_gpu = torch.jit.script(self._hasher.cuda())
         torch.jit.save(scripted_model_gpu, base_name + "_gpu.pt")
+
+    @classmethod
+    def load(cls, path, distance_func):
+        """As MultivariateBernoulli.load, for the softmax hasher (hashings.py:124-128 writes the files)."""
+        return _load_scripted(cls, path, distance_func, kwargs=lambda m: {})
 
     def train_mode(self, on):
         if on:

@@ -208,3 +208,40 @@ print("overlay ok")
                PYTHONPATH=os.pathsep.join([PKG, os.environ.get("PYTHONPATH", "")]))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "overlay ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_load_rebuilds_a_saved_hasher(tmp_path):
+    """MultivariateBernoulli.load / Categorical.load (the reference's TODO, hashings.py:58) read the
+    TorchScript files save() writes (hashings.py:53-57; eval.py:113 loads the same `_gpu.pt`)."""
+    from encoders import MultiLayerRelu, TwoLayer256Relu
+    from nlsh.hashings import Categorical, MultivariateBernoulli
+    torch.manual_seed(4)
+    x = torch.randn(9, 12)
+    cases = [(MultivariateBernoulli, MultiLayerRelu(12, [16, 8], with_batchnorm=True), {"tanh_output": True}),
+             (MultivariateBernoulli, MultiLayerRelu(12, [16], with_bias=False), {}),
+             (MultivariateBernoulli, TwoLayer256Relu(12), {}),
+             (Categorical, MultiLayerRelu(12, [16, 8]), {})]
+    for cls, enc, kw in cases:
+        h = cls(enc, 6, F.pairwise_distance, **kw)
+        h._hasher.cpu()
+        for m in h._hasher.modules():
+            if isinstance(m, nn.BatchNorm1d):
+                m.running_mean.normal_()
+                m.running_var.uniform_(0.5, 2.0)
+        h.train_mode(False)
+        path = str(tmp_path / f"{cls.__name__}_{len(list(enc.parameters()))}_cpu.pt")
+        torch.jit.save(torch.jit.script(h._hasher), path)  # what save() does for the "_cpu.pt" file
+        g = cls.load(path, F.pairwise_distance)
+        g._hasher.cpu()
+        assert type(g._hasher._encoder) is type(enc) and g._hash_size == 6
+        assert getattr(g, "_tanh_output", False) == kw.get("tanh_output", False)
+        assert not g._hasher.training
+        with torch.no_grad():
+            torch.testing.assert_close(g.predict(x), h.predict(x), rtol=0, atol=0)
+    other = nn.Sequential(nn.Linear(12, 8), nn.ReLU())  # not one of the reference's trunks
+    other.output_dim = 8
+    odd = MultivariateBernoulli(other, 4, None)
+    path = str(tmp_path / "odd_cpu.pt")
+    torch.jit.save(torch.jit.script(odd._hasher.cpu()), path)
+    with pytest.raises(NotImplementedError):
+        MultivariateBernoulli.load(path, None)
