@@ -5,8 +5,9 @@ signature and return type (precompute.py:57-67: np int array [n, k], the first h
 top-(k+1) dropped as "self"), but the 512 x N distance matrix + torch.topk per batch is
 replaced by one fused CUDA pass (nlsh_knn_bruteforce) that never materialises distances.
 `_l2` / `_cosine_distance` are kept as the selectors the reference's DISTANCE_FUNC table
-uses (precompute.py:70-76) and as plain matrix functions.  The HDF5 script part of the
-reference (precompute.py:79-100) is out of scope (no h5py here).
+uses (precompute.py:70-76) and as plain matrix functions.  The script part of the reference
+(precompute.py:79-100) reads / writes HDF5 (no h5py here); `python precompute.py <directory> <key>` does
+the same job over a directory of .npy / TEXMEX files (nlsh/data_io.py, same key names).
 """
 import numpy as np
 import torch
@@ -116,3 +117,17 @@ def nearest_exclude_positive(vectors, distance_function, positive_indexes):
     if excluded.all(dim=1).any():
         raise ValueError("nearest_exclude_positive: a row has no admissible neighbour")
     return out
+
+
+if __name__ == "__main__":
+    # precompute.py:79-100 over nlsh/data_io.py: <directory> holds train / test / neighbors as .npy or
+    # .fvecs / .ivecs / .bvecs; <key> selects the distance as in DISTANCE_FUNC; writes train_knn.npy
+    import sys
+
+    from nlsh.data_io import load_dataset, save_processed
+    if len(sys.argv) != 3 or sys.argv[2] not in DISTANCE_FUNC:
+        raise SystemExit(f"usage: python precompute.py <dataset directory> <{' | '.join(DISTANCE_FUNC)}>")
+    data = load_dataset(sys.argv[1])
+    train_knn = self_get_knn_pt(np.asarray(data["train"], dtype=np.float32), DISTANCE_FUNC[sys.argv[2]])
+    save_processed(sys.argv[1], train_knn)
+    print(f"train_knn {train_knn.shape} -> {sys.argv[1]}/train_knn.npy")
