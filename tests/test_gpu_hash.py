@@ -111,28 +111,77 @@ def test_empty_and_error_paths():
         h.hash(torch.zeros((2, 8)))
 
 
-@pytest.mark.skipif(__import__("os").environ.get("NLSH_TEST_SIREN") != "1",
-                    reason="sine trunk (encoders.py:58-79): host side pinned on the CPU, the CUDA forward with "
-                           "NLSH_ACT_SIN has not been run on a GPU yet (round 1's GPU budget ended first); "
-                           "NLSH_TEST_SIREN=1 runs it")
-def test_siren_trunk_logits_against_oracle(oracle):
-    """Hasher forward over the SIREN trunk main.py:388 builds.  sin(30 x) amplifies the rounding of the
-    first layer 30-fold, so the bar is 1e-4 of the row scale, not the 1e-5 of the ReLU trunks; codes
-    must still follow bit-exactly from the device's own logits."""
+def _fp64_logits(x, specs, native):
+    h = x.double()
+    for w, b, act, scale in specs:
+        h = h @ w.double().cpu().T
+        if b is not None:
+            h = h + b.double().cpu()
+        if act == native.ACT_RELU:
+            h = torch.relu(h)
+        elif act == native.ACT_SIN:
+            h = torch.sin(scale * h)
+    return h.numpy()
+
+
+def _row_scale_err(got, ref):
+    scale = np.maximum(np.abs(ref), np.abs(ref).max(axis=1, keepdims=True))
+    return float((np.abs(got - ref) / scale).max())
+
+
+@pytest.mark.parametrize("dims,d,hs,x_scale", [
+    ([256, 256, 64], 128, 12, 0.05),   # main.py:283,388 defaults (encoder_structure 256,256 + the 64-wide output)
+    ([256, 256], 128, 12, 0.05),
+    ([256, 256, 64], 100, 10, 0.05),   # GloVe-100 shape (cfg3)
+    ([256, 256, 64], 960, 9, 0.02),    # GIST shape (cfg5)
+    ([256, 256, 64], 128, 12, 1.0),    # unit-scale inputs: sin(30 x) of arguments up to ~200
+])
+@pytest.mark.parametrize("impl", ["default", "simt", "tc"])
+def test_siren_trunk_logits_against_oracle(oracle, dims, d, hs, x_scale, impl):
+    """Hasher forward over the SIREN trunk main.py:388 builds (encoders.py:58-79).  Bars, from the B200
+    measurements in profiles/r2_siren.jsonl:
+    * the shipped path (sine trunks take the fp32 SIMT kernels) and NLSH_MLP_IMPL=simt hold the 1e-5
+      logit bar against the fp32 oracle (measured 1.1e-6 .. 6.2e-6 of the row scale);
+    * the tcgen05 3xTF32 kernels, forced with NLSH_MLP_IMPL=tc, do not: sin(30 x) amplifies the split's
+      2^-21 error to 0.7e-5 .. 1.7e-5 (5e-5 allowed here) - which is why sine trunks are not routed there;
+    * at unit input scale no fp32 evaluation holds 1e-5: the oracle itself is 5.2e-5 away from an fp64
+      evaluation (summation order under sin(30 x)), so there the fp32 paths are held to 2x the oracle's
+      own distance from fp64 and the forced tensor-core path to 10x.
+    Codes must follow bit-exactly from the device's own logits in every case."""
+    import os
     from encoders import Siren
     from nlsh import _native
     from nlsh.hashings import MultivariateBernoulli, extract_layer_specs
     torch.manual_seed(2)
-    hashing = MultivariateBernoulli(Siren(128, [256, 256, 64]), 12, None)
+    hashing = MultivariateBernoulli(Siren(d, dims), hs, None)
     hashing.train_mode(False)
-    X = torch.randn(3000, 128) * 0.05
-    codes, _, logits = hashing.hash_tensors(X.cuda(), 1, want_logits=True)
+    X = torch.randn(3000, d) * x_scale
+    old = os.environ.pop("NLSH_MLP_IMPL", None)
+    if impl != "default":
+        os.environ["NLSH_MLP_IMPL"] = impl
+    try:
+        codes, _, logits = hashing.hash_tensors(X.cuda(), 1, want_logits=True)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("NLSH_MLP_IMPL", None)
+        if old is not None:
+            os.environ["NLSH_MLP_IMPL"] = old
     hasher = hashing._hasher
+    specs = extract_layer_specs(hasher._encoder, hasher.output_layer)
     layers = [oracle.Layer(w.cpu(), None if b is None else b.cpu(), act == _native.ACT_RELU,
-                           scale if act == _native.ACT_SIN else None)
-              for w, b, act, scale in extract_layer_specs(hasher._encoder, hasher.output_layer)]
+                           scale if act == _native.ACT_SIN else None) for w, b, act, scale in specs]
     ref = oracle.mlp_logits(X, layers).numpy()
     got = logits.cpu().numpy()
-    scale = np.maximum(np.abs(ref), np.abs(ref).max(axis=1, keepdims=True))
-    assert (np.abs(got - ref) <= 1e-4 * scale).all()
+    err = _row_scale_err(got, ref)
+    agree = float((oracle.hard_codes(torch.from_numpy(ref), oracle.HEAD_SIGMOID) == codes.cpu().numpy()).mean())
+    print(f"siren {d}->{dims}->{hs} x{x_scale} impl={impl}: max logit err {err:.3g} of the row scale, "
+          f"bucket agreement {agree:.5f}")
+    if x_scale >= 1.0:
+        ref64 = _fp64_logits(X, specs, _native)
+        own = _row_scale_err(ref, ref64)
+        assert _row_scale_err(got, ref64) <= (10.0 if impl == "tc" else 2.0) * own + 1e-5
+        assert agree >= 0.999
+    else:
+        assert err <= (5e-5 if impl == "tc" else 1e-5), err
+        assert agree >= 0.9995, agree
     assert np.array_equal(oracle.hard_codes(logits.cpu(), oracle.HEAD_SIGMOID), codes.cpu().numpy())
