@@ -144,15 +144,18 @@ int nlsh_build_csr(const int32_t* codes, int64_t n, int32_t n_buckets, const flo
  *   offsets / ids / x_sorted: the CSR produced by nlsh_build_csr (x_sorted row stride d_pad)
  *   x_sqnorm  device fp32 [n_rows] from nlsh_build_csr, or NULL.  With it (and d <= 128, k <= 32)
  *             the scan runs a tcgen05 tf32 GEMM of each row tile against the bucket's queries as
- *             a FILTER: pairs whose distance lower bound exceeds the query's current k-th best
- *             are dropped, the rest are scored exactly as below.  Results are the same either way.
+ *             a FILTER: pairs whose distance lower bound exceeds an upper bound of the query's final
+ *             k-th best distance are dropped, the rest are scored exactly as below and the k best
+ *             of them selected.  Results are the same either way.
  *   max_bucket_rows: max over buckets of offsets[c+1]-offsets[c] (host knows it from build)
  *   ids_out   device int64 [n_queries, k]  row ids (+ id_offset) by ascending distance,
  *             ties broken by smaller id; -1 past the number of candidates
  *   dists_out device fp32 [n_queries, k]   +inf past the number of candidates
  *   ncand_out device int32 [n_queries]     candidates scanned (indexer.py:71,94)
  *   flags: bit 0 = use the synchronous-staging kernel instead of the bulk-async (TMA) ring;
- *          bit 1 = do not use the tensor-core filter even when x_sqnorm is given (debug / A-B only)
+ *          bit 1 = do not use the tensor-core filter even when x_sqnorm is given (debug / A-B only);
+ *          bit 2 = tensor-core scan with candidate buffers of only k entries per query, so that
+ *                  (almost) every query takes the exact re-scan of the overflow path (tests only)
  * ------------------------------------------------------------------------------------- */
 size_t nlsh_query_workspace_bytes(int64_t n_queries, int32_t p, int32_t k, int32_t d,
                                   int32_t n_buckets, int64_t n_rows, int64_t max_bucket_rows);

@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(128)
 template <int KPL>
 __global__ void __launch_bounds__(128)
     merge_partials_kernel(const float* __restrict__ part_d, const int* __restrict__ part_id,
-                          const int* __restrict__ row_ids, const int* __restrict__ probes, const int* __restrict__ offsets,
+                          const int* __restrict__ probes, const int* __restrict__ offsets,
                           int n_buckets, int p, int k, int rchunk, int max_chunks, int dense,
                           int sqrt_scores, long long n_queries, long long id_offset,
                           long long* __restrict__ ids_out,
@@ -848,8 +848,6 @@ __global__ void __launch_bounds__(128)
         if (e < k) {
           cd = part_d[base + e];
           cid = part_id[base + e];
-          // the tensor-core scan stores row indices of x_sorted: map them to ids here
-          if (row_ids != nullptr && cid != NLSH_ID_SENTINEL) cid = row_ids[cid];
         }
         top.offer(cd, cid, cid != NLSH_ID_SENTINEL, k);
       }
@@ -865,6 +863,72 @@ __global__ void __launch_bounds__(128)
     }
   }
   if (lane == 0 && ncand_out) ncand_out[q] = ncand;
+}
+
+// Merge of the tensor-core scan (scan_tc.cu): one warp per query selects the k best (distance, id)
+// pairs of its candidate buffer.  A query whose buffer overflowed (more than `cap` rows within its
+// bound: duplicates, or a seed sample that was far too small for a skewed bucket) is re-scanned
+// exactly here, one row per lane, with the same thread-per-row arithmetic - slow, but complete.
+__global__ void __launch_bounds__(128)
+    merge_cands_kernel(const TcCand* __restrict__ cand, const int* __restrict__ cand_n, int cap,
+                       const float* __restrict__ qn, const float* __restrict__ xs,
+                       const int* __restrict__ row_ids, const int* __restrict__ probes,
+                       const int* __restrict__ offsets, int n_buckets, int p, int k, int d, int d_pad,
+                       int metric, long long n_queries, long long id_offset,
+                       long long* __restrict__ ids_out, float* __restrict__ dists_out,
+                       int* __restrict__ ncand_out, unsigned long long* __restrict__ stats) {
+  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n_queries) return;
+  const int lane = lane_id();
+  WarpTopK<1, int> top;
+  top.init(NLSH_ID_SENTINEL);
+  const int n = cand_n[q];
+  if (n <= cap) {
+    const TcCand* cq = cand + (size_t)q * cap;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int e = e0 + lane;
+      TcCand c;
+      c.d = 0.f;
+      c.id = NLSH_ID_SENTINEL;
+      if (e < n) c = cq[e];
+      if (e0 == 0)
+        top.seed32(c.d, c.id, e < n, NLSH_ID_SENTINEL, k);
+      else
+        top.offer(c.d, c.id, e < n, k);
+    }
+  }
+  int ncand = 0;
+  for (int j = 0; j < p; ++j) {
+    int b;
+    if (!probe_valid(probes, offsets, n_buckets, p, q * p + j, b)) continue;
+    const int r0 = offsets[b], r1 = offsets[b + 1];
+    ncand += r1 - r0;
+    if (n > cap) {  // warp-uniform: the exact re-scan of an overflowed query
+      TcQueryGlobal qg;
+      qg.q = qn + (size_t)q * d_pad;
+      for (int base = r0; base < r1; base += 32) {
+        const int row = base + lane;
+        float dist = 0.f;
+        int id = NLSH_ID_SENTINEL;
+        if (row < r1) {
+          dist = metric == NLSH_METRIC_L2
+                     ? tc_thread_distance<NLSH_METRIC_L2, 8>(xs + (size_t)row * d_pad, qg, d)
+                     : tc_thread_distance<NLSH_METRIC_ANGULAR, 8>(xs + (size_t)row * d_pad, qg, d);
+          id = row_ids[row];
+        }
+        top.offer(dist, id, row < r1, k);
+      }
+    }
+  }
+  if (lane < k) {
+    const int id = top.id[0];
+    ids_out[q * k + lane] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
+    dists_out[q * k + lane] = metric == NLSH_METRIC_L2 ? sqrtf(top.d[0]) : top.d[0];
+  }
+  if (lane == 0) {
+    if (ncand_out) ncand_out[q] = ncand;
+    if (stats != nullptr && n > cap) atomicAdd(stats + 5, 1ull);  // [5] queries re-scanned after an overflow
+  }
 }
 
 // Cross-shard merge (after the NCCL all-gather): lists [n_lists, n_queries, k].
@@ -1010,7 +1074,7 @@ int launch_scan_metric(int metric, const ScanArgs& a, const ScanGeom& g, bool as
   }
 }
 
-int launch_merge_partials(const float* part_d, const int* part_id, const int* row_ids, const int* probes,
+int launch_merge_partials(const float* part_d, const int* part_id, const int* probes,
                           const int* offsets, int n_buckets, int p, int k, int rchunk,
                           int max_chunks, int dense, int sqrt_scores, int64_t n_queries,
                           int64_t id_offset,
@@ -1018,24 +1082,26 @@ int launch_merge_partials(const float* part_d, const int* part_id, const int* ro
   const unsigned blocks = (unsigned)((n_queries + 3) / 4);
   long long* ids_ll = reinterpret_cast<long long*>(ids_out);
   if (k <= 32)
-    merge_partials_kernel<1><<<blocks, 128, 0, st>>>(part_d, part_id, row_ids, probes, offsets, n_buckets, p,
+    merge_partials_kernel<1><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
                                                      k, rchunk, max_chunks, dense, sqrt_scores,
                                                      n_queries, id_offset, ids_ll, dists_out, ncand_out);
   else if (k <= 64)
-    merge_partials_kernel<2><<<blocks, 128, 0, st>>>(part_d, part_id, row_ids, probes, offsets, n_buckets, p,
+    merge_partials_kernel<2><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
                                                      k, rchunk, max_chunks, dense, sqrt_scores,
                                                      n_queries, id_offset, ids_ll, dists_out, ncand_out);
   else
-    merge_partials_kernel<4><<<blocks, 128, 0, st>>>(part_d, part_id, row_ids, probes, offsets, n_buckets, p,
+    merge_partials_kernel<4><<<blocks, 128, 0, st>>>(part_d, part_id, probes, offsets, n_buckets, p,
                                                      k, rchunk, max_chunks, dense, sqrt_scores,
                                                      n_queries, id_offset, ids_ll, dists_out, ncand_out);
   return nlsh_check_cuda(nlsh_post_launch(), "merge_partials_kernel launch");
 }
 
 struct QueryWorkspace {
-  int* cnt;       // [B]   (cnt, cursor, counter are zeroed with one memset)
+  int* cnt;       // [B]   (cnt, cursor, counter, cand_n, ladder are zeroed with one memset)
   int* cursor;    // [B]
-  int* counter;   // [1]
+  int* counter;   // [64]  work-queue counter (+ the tensor-core scan's debug counters)
+  int* cand_n;    // [Q]       tensor-core scan: candidates appended per query
+  int* ladder;    // [Q * kTcLadder]  tensor-core scan: threshold ladder
   int* pair_off;  // [B+1]
   int* item_off;  // [B+1]
   int* pairs;     // [Q*p]
@@ -1046,13 +1112,36 @@ struct QueryWorkspace {
   int* part_id;
   // tensor-core scan extras
   float* qs;        // [Q*p (+ kTcNQ), d_pad] queries in pair order
-  float* qs_norm;   // [Q*p]
+  int* pq;          // [Q*p] query index of each pair
+  float* pqn2;      // [Q*p] |q|^2 of each pair's query
   float* tau_g;     // [Q]
+  float* tau0;      // [Q]
+  TcCand* cand;     // [Q * cand_cap]
+  int cand_cap;
   TcItem* tc_items; // [max_tc_items]
   int max_tc_items;
   size_t zero_ints;
   size_t total;
 };
+
+// Candidate-buffer entries per query of the tensor-core scan.  The scan appends every row whose exact
+// distance is within the query's current bound: about k * (first bucket rows / seed sample rows) from the
+// first probed bucket before the threshold ladder tightens the bound, a few from the others.  512 holds
+// that several times over for the seed sizes of nlsh_scan_tc_prepare; a query that still overflows is
+// re-scanned exactly by merge_cands_kernel.  NLSH_TC_CAND_CAP overrides (tests force overflows with it).
+int tc_cand_cap(int k) {
+  int cap = 512;
+  if (const char* env = getenv("NLSH_TC_CAND_CAP")) cap = atoi(env);
+  if (cap < k) cap = k;
+  if (cap > (1 << 16)) cap = 1 << 16;
+  return cap;
+}
+
+// Upper bound of the work items of a batch: sum_b ceil(nq_b / group) * nch_b
+// <= (pairs / group + #probed buckets) * max_chunks.  int64: the caller refuses what does not fit an int.
+int64_t item_bound(int64_t pairs, int n_buckets, int group, int max_chunks) {
+  return (pairs / group + (pairs < n_buckets ? pairs : n_buckets) + 1) * (int64_t)max_chunks;
+}
 
 // max_chunks / tc_max_chunks: chunks of the largest bucket under the SIMT / tensor-core policy
 // (tc_max_chunks = 0: no tensor-core extras).
@@ -1060,36 +1149,44 @@ QueryWorkspace carve_query_ws(void* base, int64_t nq, int p, int k, int d, int n
                               int max_chunks, int tc_max_chunks) {
   QueryWorkspace w;
   WorkspaceCarver ws(base);
-  w.zero_ints = (size_t)2 * n_buckets + 64;
+  const bool tc = tc_max_chunks > 0;
+  const size_t head = ((size_t)2 * n_buckets + 64 + 3) / 4 * 4;  // ladder rows stay 16-byte aligned
+  w.zero_ints = head + (tc ? (size_t)nq * (1 + kTcLadder) : 0);
   int* z = ws.take<int>(w.zero_ints);
   w.cnt = z;
   w.cursor = z ? z + n_buckets : nullptr;
   w.counter = z ? z + 2 * n_buckets : nullptr;
+  w.ladder = (z && tc) ? z + head : nullptr;
+  w.cand_n = (z && tc) ? z + head + (size_t)nq * kTcLadder : nullptr;
   w.pair_off = ws.take<int>((size_t)n_buckets + 1);
   w.item_off = ws.take<int>((size_t)n_buckets + 1);
   w.pairs = ws.take<int>((size_t)nq * p);
   w.qn = ws.take<float>((size_t)nq * ((d + 3) / 4 * 4));
-  // items = sum_b ceil(nq_b / kG) * nch_b <= (pairs / kG + #probed buckets) * max_chunks
   const int64_t pairs = nq * (int64_t)p;
-  int64_t mi = (pairs / kG + (pairs < n_buckets ? pairs : n_buckets) + 1) * max_chunks;
-  if (mi > (1ll << 30)) mi = 1ll << 30;
-  w.max_items = (int)mi;
+  const int64_t item_cap = 1ll << 30;  // nlsh_query_scan_topk refuses batches beyond it
+  int64_t mi = item_bound(pairs, n_buckets, kG, max_chunks);
+  w.max_items = (int)(mi < item_cap ? mi : item_cap);
   w.items = ws.take<ItemRec>((size_t)w.max_items);
-  const int list_chunks = max_chunks > tc_max_chunks ? max_chunks : tc_max_chunks;
-  const size_t lists = (size_t)nq * p * list_chunks * k;
+  const size_t lists = (size_t)nq * p * max_chunks * k;  // partial lists of the SIMT scan
   w.part_d = ws.take<float>(lists);
   w.part_id = ws.take<int>(lists);
-  w.qs = w.qs_norm = w.tau_g = nullptr;
+  w.qs = w.pqn2 = w.tau_g = w.tau0 = nullptr;
+  w.pq = nullptr;
+  w.cand = nullptr;
+  w.cand_cap = 0;
   w.tc_items = nullptr;
   w.max_tc_items = 0;
-  if (tc_max_chunks > 0) {
+  if (tc) {
     const size_t d_pad = (size_t)((d + 3) / 4 * 4);
     w.qs = ws.take<float>((size_t)(pairs + kTcNQ) * d_pad);
-    w.qs_norm = ws.take<float>((size_t)pairs + kTcNQ);
+    w.pq = ws.take<int>((size_t)pairs + kTcNQ);
+    w.pqn2 = ws.take<float>((size_t)pairs + kTcNQ);
     w.tau_g = ws.take<float>((size_t)nq);
-    int64_t mt = (pairs / kTcNQ + (pairs < n_buckets ? pairs : n_buckets) + 1) * tc_max_chunks;
-    if (mt > (1ll << 30)) mt = 1ll << 30;
-    w.max_tc_items = (int)mt;
+    w.tau0 = ws.take<float>((size_t)nq);
+    w.cand_cap = tc_cand_cap(k);
+    w.cand = ws.take<TcCand>((size_t)nq * w.cand_cap);
+    mi = item_bound(pairs, n_buckets, kTcNQ, tc_max_chunks);
+    w.max_tc_items = (int)(mi < item_cap ? mi : item_cap);
     w.tc_items = ws.take<TcItem>((size_t)w.max_tc_items);
   }
   w.total = ws.total();
@@ -1187,6 +1284,14 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   const bool tc_sized = scan_use_tc(d, k, NLSH_METRIC_L2);
   ScanPolicy pol_tc = pol_simt;
   if (tc_sized) pol_tc = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows, kTcNQ, 1);
+  {
+    const int64_t pairs64 = n_queries * (int64_t)p;
+    const int64_t need_items = item_bound(pairs64, n_buckets, kG, pol_simt.max_chunks);
+    const int64_t need_tc = tc_sized ? item_bound(pairs64, n_buckets, kTcNQ, pol_tc.max_chunks) : 0;
+    NLSH_REQUIRE(need_items < (1ll << 30) && need_tc < (1ll << 30),
+                 "query: batch of %lld queries x %d probes needs %lld work items (limit 2^30): split the batch",
+                 (long long)n_queries, p, (long long)(need_items > need_tc ? need_items : need_tc));
+  }
   const QueryWorkspace w = carve_query_ws(workspace, n_queries, p, k, d, n_buckets, pol_simt.max_chunks,
                                           tc_sized ? pol_tc.max_chunks : 0);
   if (workspace == nullptr || workspace_bytes < w.total) {
@@ -1224,38 +1329,46 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
                                                              pol.rchunk, pol.max_chunks, w.tc_items,
                                                              w.max_tc_items);
     NLSH_CUDA_TRY(nlsh_post_launch());
-    int rc = nlsh_scan_tc_prepare(w.qn, w.pairs, w.pair_off + n_buckets, n_pairs, p, geom.d_pad, w.qs,
-                                  w.qs_norm, w.tau_g, n_queries, probes, offsets, x_sorted, n_rows,
+    int rc = nlsh_scan_tc_prepare(w.qn, w.pairs, w.pair_off + n_buckets, n_pairs, p, geom.d_pad, w.qs, w.pq,
+                                  w.pqn2, w.tau_g, w.tau0, n_queries, probes, offsets, x_sorted, n_rows,
                                   n_buckets, geom.d, k, metric, st);
     if (rc != NLSH_OK) return rc;
+    unsigned long long* stats =
+        getenv("NLSH_TC_STATS") ? reinterpret_cast<unsigned long long*>(w.counter + 2) : nullptr;
+    const char* lad = getenv("NLSH_TC_LADDER");  // NLSH_TC_LADDER=0: seed bound only (A/B runs)
+    int cap = w.cand_cap;
+    if ((flags & 4u) != 0 && cap > k) cap = k;  // tests: tiny candidate buffers force the overflow re-scan
     TcScanArgs t{};
     t.xs = x_sorted;
     t.xnorm = x_sqnorm;
+    t.ids = ids;
     t.qs = w.qs;
-    t.qs_norm = w.qs_norm;
-    t.pairs = w.pairs;
+    t.pq = w.pq;
+    t.pqn2 = w.pqn2;
     t.items = w.tc_items;
     t.n_items = w.item_off + n_buckets;
     t.max_items = w.max_tc_items;
     t.item_counter = w.counter;
-    t.stats = getenv("NLSH_TC_STATS") ? reinterpret_cast<unsigned long long*>(w.counter + 2) : nullptr;
+    t.stats = stats;
     t.tau_g = w.tau_g;
-    t.part_d = w.part_d;
-    t.part_id = w.part_id;
+    t.tau0 = w.tau0;
+    t.ladder = (lad != nullptr && atoi(lad) == 0) ? nullptr : w.ladder;
+    t.cand_n = w.cand_n;
+    t.cand = w.cand;
+    t.cap = cap;
     t.n_rows = n_rows;
     t.n_pairs = n_pairs;
-    t.p = p;
     t.k = k;
     t.d = geom.d;
     t.d_pad = geom.d_pad;
-    t.max_chunks = pol.max_chunks;
     nlsh_profile_mark(st, true);
     rc = nlsh_scan_tc_launch(metric, t, st);
     nlsh_profile_mark(st, false);
     if (rc != NLSH_OK) return rc;
-    return launch_merge_partials(w.part_d, w.part_id, ids, probes, offsets, n_buckets, p, k, pol.rchunk,
-                                 pol.max_chunks, 0, metric == NLSH_METRIC_L2 ? 1 : 0, n_queries,
-                                 id_offset, ids_out, dists_out, ncand_out, st);
+    merge_cands_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(
+        w.cand, w.cand_n, cap, w.qn, x_sorted, ids, probes, offsets, n_buckets, p, k, geom.d, geom.d_pad,
+        metric, n_queries, id_offset, reinterpret_cast<long long*>(ids_out), dists_out, ncand_out, stats);
+    return nlsh_check_cuda(nlsh_post_launch(), "merge_cands_kernel launch");
   }
 
   ScanArgs a{};
@@ -1294,7 +1407,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   int rc = launch_scan_metric(metric, a, geom, async, grid, st);
   nlsh_profile_mark(st, false);
   if (rc != NLSH_OK) return rc;
-  return launch_merge_partials(w.part_d, w.part_id, nullptr, probes, offsets, n_buckets, p, k, pol.rchunk,
+  return launch_merge_partials(w.part_d, w.part_id, probes, offsets, n_buckets, p, k, pol.rchunk,
                                pol.max_chunks, 0, metric == NLSH_METRIC_L2 ? 1 : 0, n_queries,
                                id_offset, ids_out, dists_out, ncand_out, st);
 }
@@ -1383,7 +1496,7 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
     const int rc = nlsh_knn_tc_run(xq, n_queries, xdb, n_rows, d, metric, k, exclude_self ? 1 : 0,
                                    self_offset, scratch, t_d, t_id, st);
     if (rc != NLSH_OK) return rc;
-    return launch_merge_partials(t_d, t_id, nullptr, nullptr, nullptr, 1, 1, k, 0, n_blocks, 1, 0, n_queries,
+    return launch_merge_partials(t_d, t_id, nullptr, nullptr, 1, 1, k, 0, n_blocks, 1, 0, n_queries,
                                  id_offset, ids_out, dists_out, nullptr, st);
   }
   const KnnPlan kp = knn_plan(n_queries, n_rows);
@@ -1444,7 +1557,7 @@ extern "C" int nlsh_knn_bruteforce(const float* xq, int64_t n_queries, const flo
     fill_int_kernel<<<(unsigned)((lists + 255) / 256), 256, 0, st>>>(part_id, lists, NLSH_ID_SENTINEL);
     NLSH_CUDA_TRY(nlsh_post_launch());
   }
-  return launch_merge_partials(part_d, part_id, nullptr, nullptr, nullptr, 1, 1, k, kp.rchunk, kp.n_blocks, 1,
+  return launch_merge_partials(part_d, part_id, nullptr, nullptr, 1, 1, k, kp.rchunk, kp.n_blocks, 1,
                                metric == NLSH_METRIC_L2 ? 1 : 0, n_queries, id_offset, ids_out,
                                dists_out, nullptr, st);
 }

@@ -1,13 +1,13 @@
 """A/B of run-time switches of the tensor-core scan on a bench workload, all in one process (the
 library reads its NLSH_* switches at every launch): scan-kernel ms from the library's event ring,
-whole-call ms, survivor / wait counters (NLSH_TC_STATS), and torch.equal against the default.
+whole-call ms, survivor / candidate counters (NLSH_TC_STATS), and torch.equal against the default.
 
     python scripts/dbg_tc_variants.py [workload] [p] [rows]
 
-NLSH_SCAN_SEED (seed sample rows) and NLSH_SEED_PIPE (0 = the one-step-in-flight seed kernel) are switches
-of the shipped library; NLSH_TC_PREFETCH, NLSH_TC_SLOTS and
-NLSH_SEED_IMPL (commit 3b86946) and NLSH_SEED_ORDER (the commit after it) were experiments of round 1 that
-lost - with the current library they are ignored.  TC_VARIANTS="A=1,B=2;C=3" sets the list.
+Switches of the shipped library: NLSH_SCAN_SEED (base seed sample rows, 0 = no seed), NLSH_SCAN_SEED_DIV (the
+sample is at least 1/DIV of the query's first bucket), NLSH_TC_LADDER (0 = no threshold ladder), NLSH_TC_SLOTS
+(row-tile slot ring depth), NLSH_TC_CAND_CAP (candidate buffer entries per query), NLSH_SCAN_IMPL=simt (the fp32
+SIMT kernel).  TC_VARIANTS="A=1,B=2;C=3" sets the list.
 """
 import os, sys, json, torch
 sys.path.insert(0, "neural-locality-sensitive-hashing_b200"); sys.path.insert(0, ".")
@@ -25,11 +25,11 @@ Q = synth.make_queries(nq, d, hs, seed, dev, sep=bench.SEP)
 hashing, _ = bench.make_hashing(d, hs, metric, seed, dev, 300)
 idx = Indexer(hashing, X, hashing.distance, metric=metric)
 probes = idx.hash_tensors(Q, p)
-SWITCHES = ("NLSH_TC_PREFETCH", "NLSH_TC_SLOTS", "NLSH_SCAN_SEED", "NLSH_SEED_IMPL", "NLSH_SEED_ORDER", "NLSH_SEED_PIPE", "NLSH_TC_STATS")
+SWITCHES = ("NLSH_TC_SLOTS", "NLSH_SCAN_SEED", "NLSH_SCAN_SEED_DIV", "NLSH_TC_LADDER", "NLSH_TC_CAND_CAP", "NLSH_SCAN_IMPL",
+            "NLSH_TC_STATS")
 VARIANTS = [{}] + [dict(kv.split("=") for kv in v.split(",")) for v in os.environ.get(
-    "TC_VARIANTS", "NLSH_TC_PREFETCH=1;NLSH_TC_PREFETCH=2;NLSH_TC_SLOTS=6;NLSH_TC_SLOTS=5;"
-    "NLSH_TC_PREFETCH=1,NLSH_TC_SLOTS=5;NLSH_TC_PREFETCH=2,NLSH_TC_SLOTS=5;"
-    "NLSH_TC_PREFETCH=1,NLSH_SCAN_SEED=128;NLSH_TC_PREFETCH=2,NLSH_SCAN_SEED=128").split(";")] + [{}]
+    "TC_VARIANTS", "NLSH_TC_LADDER=0;NLSH_SCAN_SEED=128;NLSH_SCAN_SEED=256;NLSH_SCAN_SEED=512;NLSH_TC_SLOTS=6;"
+    "NLSH_SCAN_IMPL=simt").split(";")] + [{}]
 
 
 def set_env(v):
@@ -47,10 +47,10 @@ def stats():
     _, _, nc = run(); torch.cuda.synchronize()
     ws = list(_native._workspaces.values())[0]
     B = 1 << hs
-    st = ws.view(torch.uint8)[(2 * B + 2) * 4:(2 * B + 2) * 4 + 18 * 8].view(torch.int64).cpu().tolist()
+    st = ws.view(torch.uint8)[(2 * B + 2) * 4:(2 * B + 2) * 4 + 6 * 8].view(torch.int64).cpu().tolist()
     os.environ.pop("NLSH_TC_STATS")
-    return {"survivors": st[0], "pairs": int(nc.long().sum()), "producer": st[2:6], "mma": st[6:10],
-            "filter": st[10:14], "rerank": st[14:18]}
+    return {"pairs": int(nc.long().sum()), "survivors": st[0], "full_batches": st[1], "item_end_batches": st[2],
+            "candidates": st[3], "overflow_rescans": st[5]}
 
 
 base = None

@@ -153,6 +153,21 @@ def test_tensor_core_filter_is_exact(monkeypatch, n, d, hs, nq, p, k, metric, ki
     assert torch.equal(ids, ids2), (ids != ids2).sum().item()
     assert torch.equal(dists, dists2)
     assert (ids[:, 0] >= 0).all()
+    # the same through the filter's other regimes: candidate buffers of k entries (almost every query
+    # overflows and is re-scanned exactly in the merge), no threshold ladder (seed bound only), no seed
+    # (bound +inf: every row is scored)
+    for flags, env in ((4, {}), (0, {"NLSH_TC_LADDER": "0"}), (0, {"NLSH_SCAN_SEED": "0"})):
+        if env.get("NLSH_SCAN_SEED") == "0" and n * nq * p > 2e9:
+            continue  # scoring every pair one thread at a time is only for the small cases
+        for name, val in env.items():
+            monkeypatch.setenv(name, val)
+        idx.scan_flags = flags
+        ids3, dists3, ncand3 = idx.query_tensors(Q.cuda(), k=k, probes=probes)
+        for name in env:
+            monkeypatch.delenv(name)
+        assert torch.equal(ncand, ncand3), (flags, env)
+        assert torch.equal(ids2, ids3), (flags, env, (ids2 != ids3).sum().item())
+        assert torch.equal(dists2, dists3), (flags, env)
 
 
 def test_edge_cases(oracle):
