@@ -127,23 +127,63 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+class Workspace:
+    """Scratch memory for the library calls of ONE stream (or one captured CUDA graph).
+
+    The C ABI's contract is caller-owned, stream-ordered scratch (the library never allocates): two
+    calls may share a buffer only if they are ordered on the same stream.  A Workspace therefore binds
+    to the first stream it is used on and refuses any other; it grows on demand, and the buffer it
+    outgrows is handed back to the allocator only after that stream has passed it (record_stream).
+    `nlsh.indexer.GraphedQuery` owns a private one: the kernels captured in its graph hold raw pointers
+    into it, so nothing else may write there between replays."""
+
+    def __init__(self, device, name="anonymous"):
+        self.device = torch.device(device)
+        self.name = name
+        self.buf = None
+        self.stream_id = None
+        self.frozen = False  # set once a CUDA graph has captured pointers into buf
+
+    def get(self, nbytes):
+        stream = torch.cuda.current_stream(self.device)
+        if self.stream_id is None:
+            self.stream_id = stream.cuda_stream
+        elif self.stream_id != stream.cuda_stream:
+            raise RuntimeError(
+                f"nlsh workspace {self.name!r} belongs to stream {self.stream_id:#x} but is used on "
+                f"stream {stream.cuda_stream:#x}: concurrent streams need a Workspace each")
+        if self.buf is None or self.buf.numel() < nbytes:
+            if self.frozen:
+                raise RuntimeError(
+                    f"nlsh workspace {self.name!r} is captured in a CUDA graph and cannot grow "
+                    f"({self.buf.numel()} -> {nbytes} bytes): capture a new graph for the new shape")
+            if self.buf is not None:
+                self.buf.record_stream(stream)  # kernels already enqueued may still use the old buffer
+            self.buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
 _workspaces = {}
+_workspaces_lock = threading.Lock()
 
 
-def _workspace(device, nbytes):
-    """A cached, growing scratch buffer per device (the library never allocates)."""
-    key = (device.type, device.index)
-    buf = _workspaces.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = None
-        _workspaces.pop(key, None)
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = buf
-    return buf
+def _workspace(device, nbytes, workspace=None):
+    """The scratch buffer of this call: the caller's Workspace, or the cached one of
+    (device, current stream) - calls on different streams never share scratch."""
+    if workspace is None:
+        stream = torch.cuda.current_stream(device)
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device(),
+               stream.cuda_stream)
+        with _workspaces_lock:
+            workspace = _workspaces.get(key)
+            if workspace is None:
+                workspace = _workspaces[key] = Workspace(device, name=f"stream {stream.cuda_stream:#x}")
+    return workspace.get(nbytes)
 
 
 def release_workspaces():
-    _workspaces.clear()
+    with _workspaces_lock:
+        _workspaces.clear()
 
 
 def _f32c(t, name):
@@ -201,7 +241,7 @@ def _layer_array(layers):
     return arr
 
 
-def mlp_hash(x, layers, head, want_logits=True, want_codes=True):
+def mlp_hash(x, layers, head, want_logits=True, want_codes=True, workspace=None):
     """x [n, d] -> (logits [n, hs] fp32 | None, codes [n] int32 | None)."""
     x = _f32c(x, "x")
     n, d = x.shape
@@ -211,7 +251,7 @@ def mlp_hash(x, layers, head, want_logits=True, want_codes=True):
     codes = torch.empty((n,), dtype=torch.int32, device=x.device) if want_codes else None
     with torch.cuda.device(x.device):
         nbytes = lib().nlsh_mlp_workspace_bytes(n, arr, len(layers))
-        ws = _workspace(x.device, nbytes)
+        ws = _workspace(x.device, nbytes, workspace)
         rc = lib().nlsh_mlp_hash_f32(_ptr(x), n, d, arr, len(layers), head, _ptr(logits),
                                      _ptr(codes), _ptr(ws), ws.numel(), _stream())
     _check(rc, "nlsh_mlp_hash_f32")
@@ -245,7 +285,7 @@ def padded_dim(d):
     return (d + 3) // 4 * 4
 
 
-def build_csr(codes, n_buckets, x=None, want_sqnorm=False):
+def build_csr(codes, n_buckets, x=None, want_sqnorm=False, workspace=None):
     """codes int32 [n] in [0, n_buckets) -> (offsets int32 [B+1], ids int32 [n], x_sorted|None)
     [, x_sqnorm fp32 [n] when want_sqnorm: |x_sorted row|^2, the tensor-core scan filter's input]."""
     require_cuda(codes, "codes")
@@ -269,7 +309,7 @@ def build_csr(codes, n_buckets, x=None, want_sqnorm=False):
         xn = torch.empty((n,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         nbytes = lib().nlsh_build_workspace_bytes(n, n_buckets)
-        ws = _workspace(dev, nbytes)
+        ws = _workspace(dev, nbytes, workspace)
         rc = lib().nlsh_build_csr(_ptr(codes), n, n_buckets, _ptr(x), d, _ptr(offsets), _ptr(ids),
                                   _ptr(xs), _ptr(xn), _ptr(ws), ws.numel(), _stream())
     _check(rc, "nlsh_build_csr")
@@ -282,7 +322,7 @@ def build_csr(codes, n_buckets, x=None, want_sqnorm=False):
 # query / kNN / merge
 # --------------------------------------------------------------------------------------
 def query_scan_topk(xq, probes, offsets, ids, x_sorted, d, max_bucket_rows, metric, k,
-                    id_offset=0, flags=0, out=None, x_sqnorm=None):
+                    id_offset=0, flags=0, out=None, x_sqnorm=None, workspace=None):
     """-> (ids int64 [Q, k], dists fp32 [Q, k], n_cand int32 [Q]); `out` = preallocated
     contiguous (ids, dists, n_cand) tensors to write into; x_sqnorm (from build_csr) enables the
     tensor-core filtered scan."""
@@ -307,7 +347,7 @@ def query_scan_topk(xq, probes, offsets, ids, x_sorted, d, max_bucket_rows, metr
         out_n = torch.empty((nq,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         nbytes = lib().nlsh_query_workspace_bytes(nq, p, k, d, n_buckets, n_rows, max_bucket_rows)
-        ws = _workspace(dev, nbytes)
+        ws = _workspace(dev, nbytes, workspace)
         rc = lib().nlsh_query_scan_topk(_ptr(xq), nq, d, _ptr(probes), p, _ptr(offsets), n_buckets,
                                         _ptr(ids), _ptr(x_sorted), _ptr(x_sqnorm), n_rows,
                                         max_bucket_rows, metric,
@@ -322,7 +362,7 @@ def scan_impl(d, k, metric, has_sqnorm=True, n_queries=1 << 20, p=1, n_buckets=1
     return int(lib().nlsh_query_scan_impl(d, k, metric, 1 if has_sqnorm else 0, n_queries, p, n_buckets))
 
 
-def knn_bruteforce(xq, xdb, metric, k, exclude_self=False, self_offset=0, id_offset=0):
+def knn_bruteforce(xq, xdb, metric, k, exclude_self=False, self_offset=0, id_offset=0, workspace=None):
     """Exact kNN of xq [Q, d] in xdb [N, d] -> (ids int64 [Q, k], dists fp32 [Q, k])."""
     xq = _f32c(xq, "xq")
     xdb = _f32c(xdb, "xdb")
@@ -342,7 +382,7 @@ def knn_bruteforce(xq, xdb, metric, k, exclude_self=False, self_offset=0, id_off
     out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         nbytes = lib().nlsh_knn_workspace_bytes(nq, n, d, k)
-        ws = _workspace(dev, nbytes)
+        ws = _workspace(dev, nbytes, workspace)
         rc = lib().nlsh_knn_bruteforce(_ptr(xq), nq, _ptr(xdb), n, d, metric, k,
                                        1 if exclude_self else 0, self_offset, id_offset,
                                        _ptr(out_ids), _ptr(out_d), _ptr(ws), ws.numel(), _stream())

@@ -223,7 +223,7 @@ class MultivariateBernoulli:
     def layer_specs(self):
         return extract_layers(self._hasher._encoder, self._hasher.output_layer)
 
-    def hash_tensors(self, query_vectors, n=1, want_logits=False):
+    def hash_tensors(self, query_vectors, n=1, want_logits=False, workspace=None):
         """-> (codes int32 [B], probes int32 [B, n] | None, logits fp32 [B, hs] | None).
 
         codes[i] is the hard code (`probs > 0.5`, hashings.py:72); probes[i, 0] == codes[i]
@@ -232,7 +232,7 @@ class MultivariateBernoulli:
             raise ValueError(f"`n` should be positive integer, but got {n}")
         need_logits = want_logits or n > 1
         logits, codes = _native.mlp_hash(query_vectors, self.layer_specs(), self.head,
-                                         want_logits=need_logits, want_codes=True)
+                                         want_logits=need_logits, want_codes=True, workspace=workspace)
         probes = _native.topp_probes(logits, self.head, n) if n > 1 else None
         return codes, probes, (logits if want_logits else None)
 
@@ -307,12 +307,12 @@ class Categorical:
     def layer_specs(self):
         return extract_layers(self._hasher._encoder, self._hasher.output_layer)
 
-    def hash_tensors(self, query_vectors, n=1, want_logits=False):
+    def hash_tensors(self, query_vectors, n=1, want_logits=False, workspace=None):
         if n < 1:
             raise ValueError(f"`n` should be positive integer, but got {n}")
         need_logits = want_logits or n > 1
         logits, codes = _native.mlp_hash(query_vectors, self.layer_specs(), self.head,
-                                         want_logits=need_logits, want_codes=True)
+                                         want_logits=need_logits, want_codes=True, workspace=workspace)
         probes = _native.topp_probes(logits, self.head, n) if n > 1 else None
         return codes, probes, (logits if want_logits else None)
 

@@ -184,9 +184,12 @@ class Indexer:
         return np.diff(self._offsets_host)
 
     # ---- hash ----------------------------------------------------------------------------
-    def hash_tensors(self, query_vectors, hash_times=1):
+    def hash_tensors(self, query_vectors, hash_times=1, workspace=None):
         """-> probes int32 [n, hash_times] on the device (column 0 = hard code)."""
-        codes, probes, _ = self._hashing.hash_tensors(query_vectors, hash_times)
+        if workspace is None:
+            codes, probes, _ = self._hashing.hash_tensors(query_vectors, hash_times)
+        else:  # a hashing object from elsewhere (e.g. the reference's own class) need not know the keyword
+            codes, probes, _ = self._hashing.hash_tensors(query_vectors, hash_times, workspace=workspace)
         if probes is None:
             probes = codes.unsqueeze(1)
         if self.compat_tail_single_probe and hash_times > 1:
@@ -203,18 +206,19 @@ class Indexer:
         return codes_to_sets(self.hash_tensors(query_vectors, hash_times))
 
     # ---- query ---------------------------------------------------------------------------
-    def query_tensors(self, query_vectors, k=10, hash_times=10, probes=None, out=None):
+    def query_tensors(self, query_vectors, k=10, hash_times=10, probes=None, out=None, workspace=None):
         """Batched search -> (ids int64 [Q, k], dists fp32 [Q, k], n_candidates int32 [Q]),
         all on the device, no host synchronisation.  ids are -1 / dists +inf past the number
         of candidates.  `probes` (int32 [Q, p], -1 = unused) overrides the hasher's probe
-        sets, e.g. with the reference's sampled sets for differential testing."""
+        sets, e.g. with the reference's sampled sets for differential testing.  `workspace`: a
+        _native.Workspace for the calls' scratch (default: the one of the current stream)."""
         _native.require_cuda(query_vectors, "query_vectors")
         if probes is None:
-            probes = self.hash_tensors(query_vectors, hash_times)
+            probes = self.hash_tensors(query_vectors, hash_times, workspace=workspace)
         return _native.query_scan_topk(
             query_vectors, probes, self._offsets, self._ids, self._x_sorted, self._dim,
             self._max_bucket_rows, self._metric, k, id_offset=self._id_offset,
-            flags=self.scan_flags, out=out, x_sqnorm=self._x_sqnorm)
+            flags=self.scan_flags, out=out, x_sqnorm=self._x_sqnorm, workspace=workspace)
 
     def query(self, query_vectors, k=10, hash_times=10, probes=None) -> List[List[int]]:
         # indexer.py:56-96: returns (List[List[int]] ids by ascending distance, List[int]
@@ -255,25 +259,35 @@ class GraphedQuery:
     hasher's live parameter tensors and the index arrays in place; build a new one after the
     index is rebuilt.  Call with a CUDA (or pinned host) tensor [n_queries, d]; returns the
     graph's static output tensors (ids int64 [Q, k], dists fp32 [Q, k], n_candidates int32 [Q]),
-    overwritten by the next call."""
+    overwritten by the next call.
+
+    The graph owns its scratch (a private _native.Workspace): the captured kernels hold raw
+    pointers into it, so no other call can write there, and several GraphedQuery objects of one
+    index can replay concurrently on different streams (nlsh.parallel.PipelinedSearch does)."""
 
     def __init__(self, indexer, n_queries, k=10, hash_times=10, out=None):
         dev = indexer._candidate_vectors_gpu.device
         self.indexer = indexer
         self.q = torch.zeros((n_queries, indexer._dim), dtype=torch.float32, device=dev)
+        self.workspace = _native.Workspace(dev, name=f"GraphedQuery {id(self):#x}")
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):  # warm-up off the capture stream (sizes the workspace)
+        with torch.cuda.stream(side):  # warm-up on the capture stream (sizes the workspace)
             for _ in range(2):
-                indexer.query_tensors(self.q, k, hash_times, out=out)
+                indexer.query_tensors(self.q, k, hash_times, out=out, workspace=self.workspace)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         launches0 = _native.kernel_launch_count()
-        with torch.cuda.graph(self.graph):
-            self.ids, self.dists, self.ncand = indexer.query_tensors(self.q, k, hash_times, out=out)
+        with torch.cuda.graph(self.graph, stream=side):
+            self.ids, self.dists, self.ncand = indexer.query_tensors(self.q, k, hash_times, out=out,
+                                                                      workspace=self.workspace)
         self.kernels_per_replay = _native.kernel_launch_count() - launches0
-        # the captured kernels hold raw pointers into the scratch buffer: keep it alive
-        self._keepalive = _native._workspaces.get((dev.type, dev.index))
+        self.workspace.frozen = True
+
+    def replay(self):
+        """Replays on the current stream with whatever self.q holds."""
+        self.graph.replay()
+        return self.ids, self.dists, self.ncand
 
     def __call__(self, query_vectors):
         self.q.copy_(query_vectors, non_blocking=True)

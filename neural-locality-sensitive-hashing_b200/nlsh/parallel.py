@@ -74,6 +74,7 @@ class ShardedIndexer:
         self.shard_lo = int(shard_lo)
         self.local = Indexer(hashing, local_vectors_gpu, distance_func, metric=metric,
                              id_offset=self.shard_lo)
+        self._packed = {}  # (n_queries, k, stream) -> PackedLists of the eager path
 
     def _multi(self):
         return dist.is_initialized() and dist.get_world_size(self.group) > 1
@@ -81,8 +82,11 @@ class ShardedIndexer:
     def query_tensors(self, query_vectors, k=10, hash_times=10, probes=None):
         if not self._multi():
             return self.local.query_tensors(query_vectors, k, hash_times, probes)
-        packed = PackedLists(query_vectors.shape[0], k, dist.get_world_size(self.group),
-                             query_vectors.device)
+        dev = query_vectors.device
+        key = (query_vectors.shape[0], k, torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0)
+        packed = self._packed.get(key)
+        if packed is None:  # exchange buffers are kept per batch shape (and stream), not allocated per call
+            packed = self._packed[key] = PackedLists(key[0], k, dist.get_world_size(self.group), dev)
         self.local.query_tensors(query_vectors, k, hash_times, probes, out=packed.out())
         return packed.exchange_and_merge(self.group)
 
@@ -116,55 +120,67 @@ class ShardedIndexer:
 
 
 class PipelinedSearch:
-    """Host-to-host serving loop over a captured query graph (ShardedIndexer.capture_query) for a
-    fixed batch shape: pinned host queries in, pinned host results out, `depth` batches in flight.
-    The host-to-device copy of batch i+1 runs on a side stream while batch i is searched; the
-    device-to-host copies of a batch's results follow its search on the main stream.
+    """Serving loop over captured query graphs (ShardedIndexer.capture_query) for a fixed batch
+    shape, `depth` batches in flight, each in its own lane: a CUDA stream with its own captured
+    graph, scratch workspace, input buffer and (pinned) result buffers.  A lane runs the whole
+    life of a batch - input copy, hash -> probe selection -> plan -> seed -> scan -> merge,
+    (all-gather + shard merge), result copy - and lanes overlap on the device, so the launch-bound
+    front part of batch i+1 and the exchange of batch i run beside the scan of the other lane.
+    Batches complete in submission order per lane; results are identical to the serial path.
 
         pipe = PipelinedSearch(index, n_queries, k=10, hash_times=8)
-        t = pipe.submit(q_pinned)              # enqueue; returns a ticket, does not block
-        ids, dists, ncand = pipe.result(t)     # blocks until that batch's results are on the host
-                                               # (pinned buffers, reused `depth` submits later)
+        t = pipe.submit(q)                     # q: pinned host or device tensor; does not block
+        ids, dists, ncand = pipe.result(t)     # blocks until that batch is done; pinned host buffers
+                                               # (to_host=True) or the lane's device tensors, both
+                                               # reused `depth` submits later
     """
 
-    def __init__(self, sharded_index, n_queries, k=10, hash_times=10, depth=2):
+    def __init__(self, sharded_index, n_queries, k=10, hash_times=10, depth=2, to_host=True):
         local = sharded_index.local
         dev = local._candidate_vectors_gpu.device
-        self.run = sharded_index.capture_query(n_queries, k=k, hash_times=hash_times)
+        self.device = dev
         self.depth = int(depth)
-        self.copy_stream = torch.cuda.Stream(device=dev)
-        self.q_dev = [torch.empty((n_queries, local._dim), dtype=torch.float32, device=dev)
-                      for _ in range(self.depth)]
+        self.to_host = bool(to_host)
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.depth)]
+        self.runs = []
+        for st in self.streams:
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(st):
+                self.runs.append(sharded_index.capture_query(n_queries, k=k, hash_times=hash_times))
+        torch.cuda.synchronize(dev)
         self.out = [(torch.empty((n_queries, k), dtype=torch.int64).pin_memory(),
                      torch.empty((n_queries, k), dtype=torch.float32).pin_memory(),
-                     torch.empty((n_queries,), dtype=torch.int32).pin_memory()) for _ in range(self.depth)]
-        self.h2d_done = [torch.cuda.Event() for _ in range(self.depth)]
-        self.consumed = [torch.cuda.Event() for _ in range(self.depth)]
-        self.d2h_done = [torch.cuda.Event() for _ in range(self.depth)]
+                     torch.empty((n_queries,), dtype=torch.int32).pin_memory()) if self.to_host else None
+                    for _ in range(self.depth)]
+        self.dev_out = [None] * self.depth
+        self.done = [torch.cuda.Event() for _ in range(self.depth)]
         self.submitted = 0
         self.h2d_bytes = n_queries * local._dim * 4
         self.d2h_bytes = n_queries * k * 12 + n_queries * 4
-        self.kernels_per_call = getattr(self.run, "kernels_per_call", None)
+        self.kernels_per_call = getattr(self.runs[0], "kernels_per_call", None)
 
-    def submit(self, q_pinned):
+    def submit(self, q):
         s = self.submitted % self.depth
-        main = torch.cuda.current_stream(self.q_dev[s].device)
-        if self.submitted >= self.depth:
-            self.copy_stream.wait_event(self.consumed[s])  # the slot's previous search has read q_dev[s]
-        with torch.cuda.stream(self.copy_stream):
-            self.q_dev[s].copy_(q_pinned, non_blocking=True)
-            self.h2d_done[s].record(self.copy_stream)
-        main.wait_event(self.h2d_done[s])
-        ids, dists, ncand = self.run(self.q_dev[s])
-        self.consumed[s].record(main)
-        o_ids, o_d, o_n = self.out[s]
-        o_ids.copy_(ids, non_blocking=True)
-        o_d.copy_(dists, non_blocking=True)
-        o_n.copy_(ncand, non_blocking=True)
-        self.d2h_done[s].record(main)
+        st = self.streams[s]
+        st.wait_stream(torch.cuda.current_stream(self.device))  # q may have been produced there
+        with torch.cuda.stream(st):
+            ids, dists, ncand = self.runs[s](q)  # copies q into the lane's input buffer, replays
+            self.dev_out[s] = (ids, dists, ncand)
+            if self.to_host:
+                o_ids, o_d, o_n = self.out[s]
+                o_ids.copy_(ids, non_blocking=True)
+                o_d.copy_(dists, non_blocking=True)
+                o_n.copy_(ncand, non_blocking=True)
+            self.done[s].record(st)
         self.submitted += 1
         return s
 
     def result(self, ticket):
-        self.d2h_done[ticket].synchronize()
-        return self.out[ticket]
+        self.done[ticket].synchronize()
+        return self.out[ticket] if self.to_host else self.dev_out[ticket]
+
+    def fence(self):
+        """Orders the current stream after everything submitted so far (no host wait)."""
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self.done[:min(self.submitted, self.depth)]:
+            cur.wait_event(ev)

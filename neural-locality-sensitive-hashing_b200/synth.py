@@ -19,15 +19,18 @@ def _basis(d, hs, seed, device):
     return q[:, :hs].t().contiguous().to(device)  # [hs, d] orthonormal rows
 
 
-def _block(n, d, hs, sep, sigma, basis, seed, device, want_bits=False):
+def _block(n, d, hs, sep, sigma, basis, seed, device, want_bits=False, skew=0.5):
     g = torch.Generator(device=device).manual_seed(seed)
-    bits = torch.randint(0, 2, (n, hs), generator=g, device=device, dtype=torch.int8)
+    if skew == 0.5:
+        bits = torch.randint(0, 2, (n, hs), generator=g, device=device, dtype=torch.int8)
+    else:  # skewed cluster populations: bit = 1 with probability `skew` (bucket sizes spread over decades)
+        bits = (torch.rand((n, hs), generator=g, device=device) < skew).to(torch.int8)
     x = torch.randn(n, d, generator=g, device=device) * sigma
     x.addmm_((bits.float() * 2 - 1) * (sep * sigma), basis)
     return (x, bits) if want_bits else x
 
 
-def make_database(n, d, hs, seed, device, sep=3.0, sigma=1.0, row_lo=0, row_hi=None):
+def make_database(n, d, hs, seed, device, sep=3.0, sigma=1.0, row_lo=0, row_hi=None, skew=0.5):
     """Rows [row_lo, row_hi) of the n x d database (fp32, C-contiguous) on `device`."""
     row_hi = n if row_hi is None else row_hi
     basis = _basis(d, hs, seed, device)
@@ -36,20 +39,20 @@ def make_database(n, d, hs, seed, device, sep=3.0, sigma=1.0, row_lo=0, row_hi=N
     b1 = (row_hi + BLOCK_ROWS - 1) // BLOCK_ROWS
     for b in range(b0, b1):
         lo, hi = b * BLOCK_ROWS, min((b + 1) * BLOCK_ROWS, n)
-        blk = _block(hi - lo, d, hs, sep, sigma, basis, seed * 1000 + b, device)
+        blk = _block(hi - lo, d, hs, sep, sigma, basis, seed * 1000 + b, device, skew=skew)
         s, e = max(lo, row_lo), min(hi, row_hi)
         out[s - row_lo:e - row_lo] = blk[s - lo:e - lo]
         del blk
     return out
 
 
-def make_queries(nq, d, hs, seed, device, sep=3.0, sigma=1.0):
+def make_queries(nq, d, hs, seed, device, sep=3.0, sigma=1.0, skew=0.5):
     """Held-out queries from the same mixture (the survey's `seed + 7` convention)."""
     basis = _basis(d, hs, seed, device)
-    return _block(nq, d, hs, sep, sigma, basis, (seed + 7) * 1000 + 999, device)
+    return _block(nq, d, hs, sep, sigma, basis, (seed + 7) * 1000 + 999, device, skew=skew)
 
 
-def fit_hasher(hashing, d, hs, seed, device, sep=3.0, sigma=1.0, steps=300, batch=4096, lr=2e-3):
+def fit_hasher(hashing, d, hs, seed, device, sep=3.0, sigma=1.0, steps=300, batch=4096, lr=2e-3, skew=0.5):
     """Cheap supervised surrogate for the reference's trainers (nlsh/trainers/*): Adam on the
     BCE between `hashing.predict` and the generating cluster bits of fresh mixture samples.
     Returns the final loss.  Uses only torch (autograd); the CUDA hot path is not involved."""
@@ -58,7 +61,7 @@ def fit_hasher(hashing, d, hs, seed, device, sep=3.0, sigma=1.0, steps=300, batc
     hashing.train_mode(True)
     loss = None
     for step in range(steps):
-        x, bits = _block(batch, d, hs, sep, sigma, basis, seed * 7919 + 17 + step, device, True)
+        x, bits = _block(batch, d, hs, sep, sigma, basis, seed * 7919 + 17 + step, device, True, skew=skew)
         probs = hashing.predict(x)
         if getattr(hashing, "_tanh_output", False):
             probs = probs / 2. + 0.5

@@ -1,5 +1,6 @@
-"""bench.py --impl reference (the reference's CPU flow, oracle port) on a tiny case: runs without a
-GPU, prints ONE JSON line with the contract's keys, and ranks other than 0 exit 0 without work."""
+"""bench.py --impl reference (the reference's own CPU code from baseline/_ref when that copy exists, the
+oracle port otherwise) on a tiny case: runs without a GPU, prints ONE JSON line with the contract's keys,
+uses all host threads even under torchrun's OMP_NUM_THREADS=1, and ranks other than 0 exit 0 without work."""
 import json
 import os
 import subprocess
@@ -12,7 +13,7 @@ CMD = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "-
 
 
 def test_reference_arm_prints_one_contract_line():
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")  # what torchrun exports
     out = subprocess.run(CMD, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
@@ -23,7 +24,9 @@ def test_reference_arm_prints_one_contract_line():
     assert rec["value"] > 0 and rec["steps"] == 1 and rec["dtype"] == "f32" and rec["data"] == "synthetic"
     assert rec["config"]["workload"] == "cfg1_100k_x128_16b" and rec["config"]["rows"] == 5000
     cpu = rec["cpu_baseline"]
-    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == rec["value"] and cpu["sample"]
+    have_ref = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "nlsh", "indexer.py"))
+    assert cpu["kind"] == ("reference" if have_ref else "port")
+    assert cpu["cores"] == os.cpu_count() and cpu["value"] == rec["value"] and cpu["sample"]
     assert rec["e2e"] == {"value": rec["value"], "unit": "queries/s", "h2d_bytes_per_step": 0,
                           "d2h_bytes_per_step": 0}
 
