@@ -155,7 +155,10 @@ int nlsh_build_csr(const int32_t* codes, int64_t n, int32_t n_buckets, const flo
  *   flags: bit 0 = use the synchronous-staging kernel instead of the bulk-async (TMA) ring;
  *          bit 1 = do not use the tensor-core filter even when x_sqnorm is given (debug / A-B only);
  *          bit 2 = tensor-core scan with candidate buffers of only k entries per query, so that
- *                  (almost) every query takes the exact re-scan of the overflow path (tests only)
+ *                  (almost) every query takes the exact re-scan of the overflow path (tests only);
+ *          bits 8-15 = number of SMs the tensor-core scan's persistent grid leaves free for kernels of
+ *                  other streams (batches in flight on several streams overlap the launch-bound front
+ *                  part of one batch with the scan of another; 0 = use every SM)
  * ------------------------------------------------------------------------------------- */
 size_t nlsh_query_workspace_bytes(int64_t n_queries, int32_t p, int32_t k, int32_t d,
                                   int32_t n_buckets, int64_t n_rows, int64_t max_bucket_rows);

@@ -868,8 +868,12 @@ __global__ void __launch_bounds__(128)
 // Merge of the tensor-core scan (scan_tc.cu): one warp per query selects the k best (distance, id)
 // pairs of its candidate buffer.  A query whose buffer overflowed (more than `cap` rows within its
 // bound: duplicates, or a seed sample that was far too small for a skewed bucket) is re-scanned
-// exactly here, one row per lane, with the same thread-per-row arithmetic - slow, but complete.
-__global__ void __launch_bounds__(128)
+// exactly afterwards by the whole block - every warp scores a share of the rows of the query's probed
+// buckets, one row per lane, with the same thread-per-row arithmetic, and the warps' lists are merged
+// through shared memory.  Slow, but complete.
+constexpr int kMergeWarps = 8;
+
+__global__ void __launch_bounds__(32 * kMergeWarps)
     merge_cands_kernel(const TcCand* __restrict__ cand, const int* __restrict__ cand_n, int cap,
                        const float* __restrict__ qn, const float* __restrict__ xs,
                        const int* __restrict__ row_ids, const int* __restrict__ probes,
@@ -877,57 +881,86 @@ __global__ void __launch_bounds__(128)
                        int metric, long long n_queries, long long id_offset,
                        long long* __restrict__ ids_out, float* __restrict__ dists_out,
                        int* __restrict__ ncand_out, unsigned long long* __restrict__ stats) {
-  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (q >= n_queries) return;
+  __shared__ int ovf_q[kMergeWarps];
+  __shared__ int ovf_count;
+  __shared__ float sh_d[kMergeWarps][32];
+  __shared__ int sh_id[kMergeWarps][32];
+  const int warp = threadIdx.x >> 5;
   const int lane = lane_id();
-  WarpTopK<1, int> top;
-  top.init(NLSH_ID_SENTINEL);
-  const int n = cand_n[q];
-  if (n <= cap) {
-    const TcCand* cq = cand + (size_t)q * cap;
-    for (int e0 = 0; e0 < n; e0 += 32) {
-      const int e = e0 + lane;
-      TcCand c;
-      c.d = 0.f;
-      c.id = NLSH_ID_SENTINEL;
-      if (e < n) c = cq[e];
-      if (e0 == 0)
-        top.seed32(c.d, c.id, e < n, NLSH_ID_SENTINEL, k);
-      else
-        top.offer(c.d, c.id, e < n, k);
+  if (threadIdx.x == 0) ovf_count = 0;
+  __syncthreads();
+  const long long q = (long long)blockIdx.x * kMergeWarps + warp;
+  if (q < n_queries) {  // warp-uniform
+    const int n = cand_n[q];
+    int ncand = 0;
+    for (int j = 0; j < p; ++j) {
+      int b;
+      if (probe_valid(probes, offsets, n_buckets, p, q * p + j, b)) ncand += offsets[b + 1] - offsets[b];
+    }
+    if (lane == 0 && ncand_out) ncand_out[q] = ncand;
+    if (n <= cap) {
+      WarpTopK<1, int> top;
+      top.init(NLSH_ID_SENTINEL);
+      const TcCand* cq = cand + (size_t)q * cap;
+      for (int e0 = 0; e0 < n; e0 += 32) {
+        const int e = e0 + lane;
+        TcCand c;
+        c.d = 0.f;
+        c.id = NLSH_ID_SENTINEL;
+        if (e < n) c = cq[e];
+        if (e0 == 0)
+          top.seed32(c.d, c.id, e < n, NLSH_ID_SENTINEL, k);
+        else
+          top.offer(c.d, c.id, e < n, k);
+      }
+      if (lane < k) {
+        const int id = top.id[0];
+        ids_out[q * k + lane] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
+        dists_out[q * k + lane] = metric == NLSH_METRIC_L2 ? sqrtf(top.d[0]) : top.d[0];
+      }
+    } else if (lane == 0) {
+      ovf_q[atomicAdd(&ovf_count, 1)] = (int)(q - (long long)blockIdx.x * kMergeWarps);
+      if (stats != nullptr) atomicAdd(stats + 5, 1ull);  // [5] queries re-scanned after an overflow
     }
   }
-  int ncand = 0;
-  for (int j = 0; j < p; ++j) {
-    int b;
-    if (!probe_valid(probes, offsets, n_buckets, p, q * p + j, b)) continue;
-    const int r0 = offsets[b], r1 = offsets[b + 1];
-    ncand += r1 - r0;
-    if (n > cap) {  // warp-uniform: the exact re-scan of an overflowed query
-      TcQueryGlobal qg;
-      qg.q = qn + (size_t)q * d_pad;
-      for (int base = r0; base < r1; base += 32) {
+  __syncthreads();
+  const int n_ovf = ovf_count;  // block-uniform
+  for (int o = 0; o < n_ovf; ++o) {
+    const long long oq = (long long)blockIdx.x * kMergeWarps + ovf_q[o];
+    TcQueryGlobal qg;
+    qg.q = qn + (size_t)oq * d_pad;
+    WarpTopK<1, int> top;
+    top.init(NLSH_ID_SENTINEL);
+    for (int j = 0; j < p; ++j) {
+      int b;
+      if (!probe_valid(probes, offsets, n_buckets, p, oq * p + j, b)) continue;
+      const int r0 = offsets[b], r1 = offsets[b + 1];
+      for (int base = r0 + 32 * warp; base < r1; base += 32 * kMergeWarps) {
         const int row = base + lane;
         float dist = 0.f;
         int id = NLSH_ID_SENTINEL;
         if (row < r1) {
           dist = metric == NLSH_METRIC_L2
-                     ? tc_thread_distance<NLSH_METRIC_L2, 8>(xs + (size_t)row * d_pad, qg, d)
-                     : tc_thread_distance<NLSH_METRIC_ANGULAR, 8>(xs + (size_t)row * d_pad, qg, d);
+                     ? tc_thread_distance<NLSH_METRIC_L2, 16>(xs + (size_t)row * d_pad, qg, d)
+                     : tc_thread_distance<NLSH_METRIC_ANGULAR, 16>(xs + (size_t)row * d_pad, qg, d);
           id = row_ids[row];
         }
         top.offer(dist, id, row < r1, k);
       }
     }
-  }
-  if (lane < k) {
-    const int id = top.id[0];
-    ids_out[q * k + lane] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
-    dists_out[q * k + lane] = metric == NLSH_METRIC_L2 ? sqrtf(top.d[0]) : top.d[0];
-  }
-  if (lane == 0) {
-    if (ncand_out) ncand_out[q] = ncand;
-    if (stats != nullptr && n > cap) atomicAdd(stats + 5, 1ull);  // [5] queries re-scanned after an overflow
+    sh_d[warp][lane] = top.d[0];
+    sh_id[warp][lane] = top.id[0];
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 1; w < kMergeWarps; ++w)
+        top.offer(sh_d[w][lane], sh_id[w][lane], sh_id[w][lane] != NLSH_ID_SENTINEL, k);
+      if (lane < k) {
+        const int id = top.id[0];
+        ids_out[oq * k + lane] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
+        dists_out[oq * k + lane] = metric == NLSH_METRIC_L2 ? sqrtf(top.d[0]) : top.d[0];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -1361,11 +1394,12 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
     t.k = k;
     t.d = geom.d;
     t.d_pad = geom.d_pad;
+    t.sm_reserve = (int)((flags >> 8) & 0xffu);
     nlsh_profile_mark(st, true);
     rc = nlsh_scan_tc_launch(metric, t, st);
     nlsh_profile_mark(st, false);
     if (rc != NLSH_OK) return rc;
-    merge_cands_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(
+    merge_cands_kernel<<<(unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps), 32 * kMergeWarps, 0, st>>>(
         w.cand, w.cand_n, cap, w.qn, x_sorted, ids, probes, offsets, n_buckets, p, k, geom.d, geom.d_pad,
         metric, n_queries, id_offset, reinterpret_cast<long long*>(ids_out), dists_out, ncand_out, stats);
     return nlsh_check_cuda(nlsh_post_launch(), "merge_cands_kernel launch");

@@ -774,7 +774,12 @@ int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {
   if ((rc = tc_make_map(&map_x, a.xs, a.n_rows, a.d_pad, kTile)) != NLSH_OK) return rc;
   if ((rc = tc_make_map(&map_x32, a.xs, a.n_rows, a.d_pad, 32)) != NLSH_OK) return rc;
   if ((rc = tc_make_map(&map_q, a.qs, a.n_pairs, a.d_pad, kTcNQ)) != NLSH_OK) return rc;
-  const int grid = nlsh_num_sms();
+  // One persistent CTA per SM; `sm_reserve` SMs are left to other streams (the launch-bound front part of
+  // the next batch in nlsh.parallel.PipelinedSearch).  NLSH_TC_GRID=<CTAs> overrides (A/B runs).
+  int grid = nlsh_num_sms() - a.sm_reserve;
+  if (const char* env = getenv("NLSH_TC_GRID")) grid = atoi(env);
+  if (grid < 1) grid = 1;
+  if (grid > nlsh_num_sms()) grid = nlsh_num_sms();
   if (metric == NLSH_METRIC_L2) {
     auto kern = scan_tc_kernel<NLSH_METRIC_L2>;
     NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -45,6 +45,7 @@ struct TcScanArgs {
   long long n_rows;
   long long n_pairs;
   int k, d, d_pad, kblocks, n_slots;
+  int sm_reserve;        // SMs the persistent grid leaves free (flags bits 8-15 of nlsh_query_scan_topk)
   float l2_slack;        // 2.1e-6 * sqrt(d): bound of the eps cross term of F.pairwise_distance
 };
 
