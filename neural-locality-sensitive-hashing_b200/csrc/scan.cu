@@ -23,6 +23,7 @@
 // All top-k decisions use the (distance, id) lexicographic order, so the result does not
 // depend on item scheduling or on how many GPUs the database is sharded over.
 #include <cuda.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -113,8 +114,12 @@ struct ScanPolicy {
   int max_chunks;  // chunks of the largest bucket
 };
 
+// row_bytes > 0 (the tensor-core scan): the query groups of one bucket chunk are consecutive items, picked up by
+// different CTAs at about the same time, so a chunk streamed by the first of them is an L2 hit for the others
+// only while the chunks in flight on all CTAs fit the L2 together; with several groups per bucket the chunk is
+// bounded so that they take at most a quarter of it.
 ScanPolicy scan_policy(int64_t n_queries, int p, int n_buckets, int64_t n_rows,
-                       int64_t max_bucket_rows, int group = kG, int ctas_per_sm = 2) {
+                       int64_t max_bucket_rows, int group = kG, int ctas_per_sm = 2, int64_t row_bytes = 0) {
   const int64_t grid = (int64_t)nlsh_num_sms() * ctas_per_sm;
   const int64_t target_items = grid * 8;
   const int64_t pairs = n_queries * p > 0 ? n_queries * p : 1;
@@ -126,6 +131,13 @@ ScanPolicy scan_policy(int64_t n_queries, int p, int n_buckets, int64_t n_rows,
   int64_t avg_bucket = n_rows / (n_buckets > 0 ? n_buckets : 1);
   if (avg_bucket < 1) avg_bucket = 1;
   int64_t rchunk = (avg_bucket + chunks_needed - 1) / chunks_needed;
+  const int64_t groups_per_bucket = groups / (distinct > 0 ? distinct : 1);
+  if (row_bytes > 0 && groups_per_bucket >= 2) {
+    const int64_t l2_share = 32ll << 20;
+    int64_t cap_rows = l2_share * groups_per_bucket / (grid * row_bytes);
+    if (cap_rows < 2 * kTileRows) cap_rows = 2 * kTileRows;
+    if (rchunk > cap_rows) rchunk = cap_rows;
+  }
   if (max_bucket_rows < 1) max_bucket_rows = 1;
   const int64_t floor_rchunk = (max_bucket_rows + kMaxChunksPerBucket - 1) / kMaxChunksPerBucket;
   if (rchunk < floor_rchunk) rchunk = floor_rchunk;
@@ -348,7 +360,7 @@ __global__ void plan_items_kernel(const ScanArgs a, ItemRec* __restrict__ out, i
 // Items of the tensor-core scan (scan_tc.cu): (bucket, row chunk, group of <= kTcNQ pairs).
 __global__ void plan_tc_items_kernel(const int* __restrict__ item_off, const int* __restrict__ pair_off,
                                      const int* __restrict__ offsets, int n_buckets, int rchunk,
-                                     int max_chunks, TcItem* __restrict__ out, int max_items) {
+                                     int max_chunks, int group, TcItem* __restrict__ out, int max_items) {
   int total = item_off[n_buckets];
   if (total > max_items) total = max_items;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -361,7 +373,7 @@ __global__ void plan_tc_items_kernel(const int* __restrict__ item_off, const int
     const int local = i - item_off[b];
     const int p0 = pair_off[b];
     const int nq = pair_off[b + 1] - p0;
-    const int ngroups = (nq + kTcNQ - 1) / kTcNQ;
+    const int ngroups = (nq + group - 1) / group;
     const int c = local / ngroups;
     const int gq = local - c * ngroups;
     const int r0 = offsets[b];
@@ -374,9 +386,9 @@ __global__ void plan_tc_items_kernel(const int* __restrict__ item_off, const int
     TcItem r;
     r.row0 = r0 + (int)c_lo;
     r.row1 = r0 + (int)c_hi;
-    r.pair_base = p0 + gq * kTcNQ;
-    const int left = nq - gq * kTcNQ;
-    r.nq = left < kTcNQ ? left : kTcNQ;
+    r.pair_base = p0 + gq * group;
+    const int left = nq - gq * group;
+    r.nq = left < group ? left : group;
     r.chunk = c;
     r.pad[0] = r.pad[1] = r.pad[2] = 0;
     out[i] = r;
@@ -873,18 +885,19 @@ __global__ void __launch_bounds__(128)
 // through shared memory.  Slow, but complete.
 constexpr int kMergeWarps = 8;
 
+template <int KPL>
 __global__ void __launch_bounds__(32 * kMergeWarps)
     merge_cands_kernel(const TcCand* __restrict__ cand, const int* __restrict__ cand_n, int cap,
                        const float* __restrict__ qn, const float* __restrict__ xs,
                        const int* __restrict__ row_ids, const int* __restrict__ probes,
                        const int* __restrict__ offsets, int n_buckets, int p, int k, int d, int d_pad,
-                       int metric, long long n_queries, long long id_offset,
+                       int metric, long long n_queries, long long id_offset, const float* __restrict__ tau_g,
                        long long* __restrict__ ids_out, float* __restrict__ dists_out,
                        int* __restrict__ ncand_out, unsigned long long* __restrict__ stats) {
   __shared__ int ovf_q[kMergeWarps];
   __shared__ int ovf_count;
-  __shared__ float sh_d[kMergeWarps][32];
-  __shared__ int sh_id[kMergeWarps][32];
+  __shared__ float sh_d[kMergeWarps][32 * KPL];
+  __shared__ int sh_id[kMergeWarps][32 * KPL];
   const int warp = threadIdx.x >> 5;
   const int lane = lane_id();
   if (threadIdx.x == 0) ovf_count = 0;
@@ -899,24 +912,30 @@ __global__ void __launch_bounds__(32 * kMergeWarps)
     }
     if (lane == 0 && ncand_out) ncand_out[q] = ncand;
     if (n <= cap) {
-      WarpTopK<1, int> top;
+      WarpTopK<KPL, int> top;
       top.init(NLSH_ID_SENTINEL);
       const TcCand* cq = cand + (size_t)q * cap;
+      const float bound = tau_g[q];  // the final bound: candidates appended under an earlier, looser one drop out
       for (int e0 = 0; e0 < n; e0 += 32) {
         const int e = e0 + lane;
         TcCand c;
         c.d = 0.f;
         c.id = NLSH_ID_SENTINEL;
         if (e < n) c = cq[e];
+        const bool ok = e < n && c.d <= bound;
         if (e0 == 0)
-          top.seed32(c.d, c.id, e < n, NLSH_ID_SENTINEL, k);
+          top.seed32(c.d, c.id, ok, NLSH_ID_SENTINEL, k);
         else
-          top.offer(c.d, c.id, e < n, k);
+          top.offer(c.d, c.id, ok, k);
       }
-      if (lane < k) {
-        const int id = top.id[0];
-        ids_out[q * k + lane] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
-        dists_out[q * k + lane] = metric == NLSH_METRIC_L2 ? sqrtf(top.d[0]) : top.d[0];
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const int pos = j * 32 + lane;
+        if (pos < k) {
+          const int id = top.id[j];
+          ids_out[q * k + pos] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
+          dists_out[q * k + pos] = metric == NLSH_METRIC_L2 ? sqrtf(top.d[j]) : top.d[j];
+        }
       }
     } else if (lane == 0) {
       ovf_q[atomicAdd(&ovf_count, 1)] = (int)(q - (long long)blockIdx.x * kMergeWarps);
@@ -929,7 +948,7 @@ __global__ void __launch_bounds__(32 * kMergeWarps)
     const long long oq = (long long)blockIdx.x * kMergeWarps + ovf_q[o];
     TcQueryGlobal qg;
     qg.q = qn + (size_t)oq * d_pad;
-    WarpTopK<1, int> top;
+    WarpTopK<KPL, int> top;
     top.init(NLSH_ID_SENTINEL);
     for (int j = 0; j < p; ++j) {
       int b;
@@ -948,16 +967,26 @@ __global__ void __launch_bounds__(32 * kMergeWarps)
         top.offer(dist, id, row < r1, k);
       }
     }
-    sh_d[warp][lane] = top.d[0];
-    sh_id[warp][lane] = top.id[0];
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      sh_d[warp][j * 32 + lane] = top.d[j];
+      sh_id[warp][j * 32 + lane] = top.id[j];
+    }
     __syncthreads();
     if (warp == 0) {
-      for (int w = 1; w < kMergeWarps; ++w)
-        top.offer(sh_d[w][lane], sh_id[w][lane], sh_id[w][lane] != NLSH_ID_SENTINEL, k);
-      if (lane < k) {
-        const int id = top.id[0];
-        ids_out[oq * k + lane] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
-        dists_out[oq * k + lane] = metric == NLSH_METRIC_L2 ? sqrtf(top.d[0]) : top.d[0];
+      for (int w = 1; w < kMergeWarps; ++w) {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j)
+          top.offer(sh_d[w][j * 32 + lane], sh_id[w][j * 32 + lane], sh_id[w][j * 32 + lane] != NLSH_ID_SENTINEL, k);
+      }
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const int pos = j * 32 + lane;
+        if (pos < k) {
+          const int id = top.id[j];
+          ids_out[oq * k + pos] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
+          dists_out[oq * k + pos] = metric == NLSH_METRIC_L2 ? sqrtf(top.d[j]) : top.d[j];
+        }
       }
     }
     __syncthreads();
@@ -1158,12 +1187,19 @@ struct QueryWorkspace {
 };
 
 // Candidate-buffer entries per query of the tensor-core scan.  The scan appends every row whose exact
-// distance is within the query's current bound: about k * (first bucket rows / seed sample rows) from the
-// first probed bucket before the threshold ladder tightens the bound, a few from the others.  512 holds
-// that several times over for the seed sizes of nlsh_scan_tc_prepare; a query that still overflows is
-// re-scanned exactly by merge_cands_kernel.  NLSH_TC_CAND_CAP overrides (tests force overflows with it).
-int tc_cand_cap(int k) {
+// distance is within the query's bound at that moment.  Even a bound that always equals the running k-th
+// best lets k (1 + ln(C / k)) of C candidates in random order through (the expected number of updates of a
+// streaming top-k); the seed's bound starts looser (about k * first bucket rows / sample rows pass from the
+// first bucket) and the threshold ladder tightens it in steps of 1/32.  The buffer holds 5x the streaming
+// figure for C = 2 p * (average bucket), at least 512 entries, rounded up to a power of two: 512 for config 4
+// (k = 10, C = 39k), 8192 for config 5 (k = 100, C = 500k).  A query that still overflows is re-scanned
+// exactly by merge_cands_kernel.  NLSH_TC_CAND_CAP overrides (tests force overflows with it).
+int tc_cand_cap(int k, int p, int64_t n_rows, int n_buckets) {
+  double c = 2.0 * p * (double)(n_rows / (n_buckets > 0 ? n_buckets : 1) + 1);
+  if (c < 2.0 * k) c = 2.0 * k;
+  const double want = 5.0 * k * (1.0 + log(c / k));
   int cap = 512;
+  while (cap < want && cap < (1 << 16)) cap *= 2;
   if (const char* env = getenv("NLSH_TC_CAND_CAP")) cap = atoi(env);
   if (cap < k) cap = k;
   if (cap > (1 << 16)) cap = 1 << 16;
@@ -1179,7 +1215,7 @@ int64_t item_bound(int64_t pairs, int n_buckets, int group, int max_chunks) {
 // max_chunks / tc_max_chunks: chunks of the largest bucket under the SIMT / tensor-core policy
 // (tc_max_chunks = 0: no tensor-core extras).
 QueryWorkspace carve_query_ws(void* base, int64_t nq, int p, int k, int d, int n_buckets,
-                              int max_chunks, int tc_max_chunks) {
+                              int max_chunks, int tc_max_chunks, int64_t n_rows) {
   QueryWorkspace w;
   WorkspaceCarver ws(base);
   const bool tc = tc_max_chunks > 0;
@@ -1211,12 +1247,12 @@ QueryWorkspace carve_query_ws(void* base, int64_t nq, int p, int k, int d, int n
   w.max_tc_items = 0;
   if (tc) {
     const size_t d_pad = (size_t)((d + 3) / 4 * 4);
-    w.qs = ws.take<float>((size_t)(pairs + kTcNQ) * d_pad);
-    w.pq = ws.take<int>((size_t)pairs + kTcNQ);
-    w.pqn2 = ws.take<float>((size_t)pairs + kTcNQ);
+    w.qs = ws.take<float>((size_t)(pairs + kTcNQMax) * d_pad);
+    w.pq = ws.take<int>((size_t)pairs + kTcNQMax);
+    w.pqn2 = ws.take<float>((size_t)pairs + kTcNQMax);
     w.tau_g = ws.take<float>((size_t)nq);
     w.tau0 = ws.take<float>((size_t)nq);
-    w.cand_cap = tc_cand_cap(k);
+    w.cand_cap = tc_cand_cap(k, p, n_rows, n_buckets);
     w.cand = ws.take<TcCand>((size_t)nq * w.cand_cap);
     mi = item_bound(pairs, n_buckets, kTcNQ, tc_max_chunks);
     w.max_tc_items = (int)(mi < item_cap ? mi : item_cap);
@@ -1273,6 +1309,19 @@ bool scan_batch_prefers_tc(int64_t n_queries, int32_t p, int32_t n_buckets) {
 }
 }  // namespace
 
+namespace {
+// Queries per item of the tensor-core scan: 128 when the batch puts 64 or more (query, probe) pairs on a
+// probed bucket (configs 1, 2, 5: a row tile then serves 128 queries per pass instead of 32), else 32.
+// NLSH_TC_NQ=32/128 overrides (A/B runs).
+int tc_group_size(int64_t n_queries, int32_t p, int32_t n_buckets) {
+  const int64_t pairs = n_queries * (int64_t)p;
+  const int64_t distinct = pairs < n_buckets ? pairs : n_buckets;
+  int group = (distinct > 0 && pairs >= 64 * distinct) ? kTcNQMax : kTcNQ;
+  if (const char* env = getenv("NLSH_TC_NQ")) group = atoi(env) == kTcNQMax ? kTcNQMax : kTcNQ;
+  return group;
+}
+}  // namespace
+
 extern "C" int nlsh_query_scan_impl(int32_t d, int32_t k, int32_t metric, int32_t has_sqnorm,
                                     int64_t n_queries, int32_t p, int32_t n_buckets) {
   return (has_sqnorm && scan_use_tc(d, k, metric) && scan_batch_prefers_tc(n_queries, p, n_buckets)) ? 1 : 0;
@@ -1285,8 +1334,9 @@ extern "C" size_t nlsh_query_workspace_bytes(int64_t n_queries, int32_t p, int32
   const ScanPolicy pol = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows);
   int tc_chunks = 0;  // the metric is not an argument: sized for either scan implementation
   if (scan_use_tc(d, k, NLSH_METRIC_L2))
-    tc_chunks = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows, kTcNQ, 1).max_chunks;
-  return carve_query_ws(nullptr, n_queries, p, k, d, n_buckets, pol.max_chunks, tc_chunks).total;
+    tc_chunks = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows, tc_group_size(n_queries, p, n_buckets), 1,
+                            4ll * ((d + 3) / 4 * 4)).max_chunks;
+  return carve_query_ws(nullptr, n_queries, p, k, d, n_buckets, pol.max_chunks, tc_chunks, n_rows).total;
 }
 
 extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t d,
@@ -1316,17 +1366,18 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   const ScanPolicy pol_simt = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows);
   const bool tc_sized = scan_use_tc(d, k, NLSH_METRIC_L2);
   ScanPolicy pol_tc = pol_simt;
-  if (tc_sized) pol_tc = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows, kTcNQ, 1);
+  const int tc_group = tc_group_size(n_queries, p, n_buckets);
+  if (tc_sized) pol_tc = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows, tc_group, 1, 4ll * ((d + 3) / 4 * 4));
   {
     const int64_t pairs64 = n_queries * (int64_t)p;
     const int64_t need_items = item_bound(pairs64, n_buckets, kG, pol_simt.max_chunks);
-    const int64_t need_tc = tc_sized ? item_bound(pairs64, n_buckets, kTcNQ, pol_tc.max_chunks) : 0;
+    const int64_t need_tc = tc_sized ? item_bound(pairs64, n_buckets, tc_group, pol_tc.max_chunks) : 0;
     NLSH_REQUIRE(need_items < (1ll << 30) && need_tc < (1ll << 30),
                  "query: batch of %lld queries x %d probes needs %lld work items (limit 2^30): split the batch",
                  (long long)n_queries, p, (long long)(need_items > need_tc ? need_items : need_tc));
   }
   const QueryWorkspace w = carve_query_ws(workspace, n_queries, p, k, d, n_buckets, pol_simt.max_chunks,
-                                          tc_sized ? pol_tc.max_chunks : 0);
+                                          tc_sized ? pol_tc.max_chunks : 0, n_rows);
   if (workspace == nullptr || workspace_bytes < w.total) {
     nlsh_set_error("query: workspace %zu bytes < required %zu", workspace_bytes, w.total);
     return NLSH_ERR_WORKSPACE;
@@ -1346,7 +1397,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
                                                                      n_pairs, w.cnt);
   NLSH_CUDA_TRY(nlsh_post_launch());
   plan_scan_kernel<<<1, 1024, 0, st>>>(w.cnt, offsets, n_buckets, pol.rchunk, pol.max_chunks,
-                                       use_tc ? kTcNQ : kG, w.pair_off, w.item_off);
+                                       use_tc ? tc_group : kG, w.pair_off, w.item_off);
   NLSH_CUDA_TRY(nlsh_post_launch());
   plan_scatter_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(
       probes, offsets, n_buckets, p, n_pairs, w.pair_off, w.cursor, w.pairs);
@@ -1359,7 +1410,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
 
   if (use_tc) {
     plan_tc_items_kernel<<<nlsh_num_sms() * 4, 256, 0, st>>>(w.item_off, w.pair_off, offsets, n_buckets,
-                                                             pol.rchunk, pol.max_chunks, w.tc_items,
+                                                             pol.rchunk, pol.max_chunks, tc_group, w.tc_items,
                                                              w.max_tc_items);
     NLSH_CUDA_TRY(nlsh_post_launch());
     int rc = nlsh_scan_tc_prepare(w.qn, w.pairs, w.pair_off + n_buckets, n_pairs, p, geom.d_pad, w.qs, w.pq,
@@ -1395,13 +1446,19 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
     t.d = geom.d;
     t.d_pad = geom.d_pad;
     t.sm_reserve = (int)((flags >> 8) & 0xffu);
+    t.avg_item_rows = (int)(n_rows / n_buckets);
+    t.nq_group = tc_group;
     nlsh_profile_mark(st, true);
     rc = nlsh_scan_tc_launch(metric, t, st);
     nlsh_profile_mark(st, false);
     if (rc != NLSH_OK) return rc;
-    merge_cands_kernel<<<(unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps), 32 * kMergeWarps, 0, st>>>(
-        w.cand, w.cand_n, cap, w.qn, x_sorted, ids, probes, offsets, n_buckets, p, k, geom.d, geom.d_pad,
-        metric, n_queries, id_offset, reinterpret_cast<long long*>(ids_out), dists_out, ncand_out, stats);
+    const unsigned mblocks = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
+#define NLSH_MERGE_ARGS w.cand, w.cand_n, cap, w.qn, x_sorted, ids, probes, offsets, n_buckets, p, k, geom.d, geom.d_pad, \
+                        metric, n_queries, id_offset, w.tau_g, reinterpret_cast<long long*>(ids_out), dists_out, ncand_out, stats
+    if (k <= 32) merge_cands_kernel<1><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
+    else if (k <= 64) merge_cands_kernel<2><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
+    else merge_cands_kernel<4><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
+#undef NLSH_MERGE_ARGS
     return nlsh_check_cuda(nlsh_post_launch(), "merge_cands_kernel launch");
   }
 

@@ -1,5 +1,5 @@
 // Candidate scan with a tensor-core FILTER in front of the exact distance (the default path of
-// nlsh_query_scan_topk for d <= 128, k <= 32 and batches in which bucket tiles are shared).  Same
+// nlsh_query_scan_topk for k <= 128 and batches in which bucket tiles are shared).  Same
 // job as scan.cu::scan_kernel - the per-query gather + distance_func + topk of Indexer.query
 // (nlsh/indexer.py:62-95) - and the same results: every distance that reaches a top-k list is computed
 // in fp32 in the reference's difference form (nlsh/data.py:201 F.pairwise_distance, nlsh/data.py:109
@@ -42,10 +42,10 @@
 //                  item's queries (box 32 rows x 32 fp32 per K block, SWIZZLE_128B; 4-deep item ring)
 //                  and streams the row tiles (box 128 rows x 32 fp32; 32-row boxes for the ragged last
 //                  tile of a bucket) into the slot ring, row norms alongside (bulk copy);
-//   warp 1 lane 0  MMA issuer: per tile and K block 4 x tcgen05.mma M128 N32 K8 into one of kAccSets
+//   warp 1 lane 0  MMA issuer: per tile and K block 4 x tcgen05.mma M128 N32 K8 into one of 16
 //                  TMEM accumulator sets; tcgen05.commit frees the slot, the last one of a tile
 //                  signals acc_full - a slot lives from its TMA issue to the end of its MMAs, and the
-//                  accumulator ring lets the front end run kAccSets tiles ahead of the filter;
+//                  accumulator ring lets the front end run that many tiles ahead of the filter;
 //   warps 2-9      filter + score, two groups of four (one warp per TMEM lane quarter), group g takes
 //                  the tiles with tile index = g (mod 2): tcgen05.ld the row's 32 scores (then the TMEM
 //                  set is free again), bound + compare, survivors go to the warp's PRIVATE queue in
@@ -53,6 +53,13 @@
 //                  queries leave shared memory then - the warp scores them one per lane: the row is
 //                  re-read from L2 (it has just streamed through), the query comes from the item's
 //                  shared-memory copy, candidates within the bound are appended to the query's buffer.
+//
+// Variants (template parameters): QGLOBAL - the scorer reads the query from the pair-ordered global copy
+// instead of the item's shared-memory copy; queue entries then do not refer to an item slot and nothing
+// is flushed at the end of an item (buckets of two or three tiles: 8-GPU shards).  WIDE (d_pad > 128,
+// config 5's 960-wide rows) - the queries do not fit shared memory, so the K block of the item's queries
+// travels with each K block of a row tile (a 20 KB slot: 16 KB rows + 4 KB queries, both by TMA; the queries
+// come from L2), the accumulate runs over d_pad / 32 K blocks, and the scorer is QGLOBAL.
 #include <stdlib.h>
 #include <string.h>
 
@@ -71,8 +78,8 @@ constexpr int kGroups = 2;                      // filter groups (tiles alternat
 constexpr int kFilterWarps = 4 * kGroups;       // one per TMEM lane quarter and group
 constexpr int kTile = 128;                      // rows per tile = UMMA M
 constexpr int kThreads = 64 + 32 * kFilterWarps;  // 320
-constexpr int kAccSets = 8;                     // TMEM accumulator ring (kTcNQ columns each)
-constexpr int kTmemCols = kAccSets * kTcNQ;     // 256
+constexpr int kTmemCols = 512;                  // TMEM accumulator ring: 16 sets of 32 columns or 4 sets of 128
+constexpr int kMaxAccSets = 16;
 constexpr uint32_t kSlotBytes = kTile * kTcBK * sizeof(float);   // 16 KB: one K block of a row tile
 constexpr uint32_t kSubBoxBytes = 32 * kTcBK * sizeof(float);    // 4 KB: a 32-row box of the ragged last tile
 constexpr uint32_t kQBoxBytes = kTcNQ * kTcBK * sizeof(float);   // 4 KB: one K block of the queries
@@ -82,13 +89,13 @@ constexpr uint32_t kMetaBytes = 640;            // kMetaFloats * 4 rounded up to
 constexpr int kMetaBufs = 16;                   // row-norm ring depth (tiles)
 constexpr int kItemBufs = 4;                    // item ring depth: buckets of a few tiles are shorter than the
                                                 // pipeline, so several items must be in flight
-constexpr int kMaxKBlocks = 4;                  // d_pad <= 128
+constexpr int kMaxKBlocks = 4;                  // d_pad <= 128: the item's queries stay in shared memory
+constexpr int kMaxWideKBlocks = 128;            // WIDE: d_pad <= 4096
 constexpr int kQueueCap = 64;                   // per-warp survivor queue (a power of two >= 2 * 32)
 constexpr float kFilterC = 0.001953125f * 1.02f + 4e-5f;  // see header comment
 constexpr float kAngularC = 2.1e-3f;
 
 static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation: power of two <= 512");
-static_assert(kAccSets % kGroups == 0, "an accumulator set must always belong to the same filter group");
 static_assert(kMetaBufs % kGroups == 0, "a row-norm buffer must always belong to the same filter group");
 
 __device__ __forceinline__ float pos_inf() { return __int_as_float(0x7f800000); }
@@ -122,11 +129,11 @@ struct TcQueryShared {
 };
 
 struct SmemLayout {
-  unsigned char* slots;   // [n_slots][16 KB]
-  unsigned char* qbuf;    // [kItemBufs][kblocks][4 KB]
+  unsigned char* slots;   // [n_slots][16 KB (+ NQ * 128 bytes of queries, WIDE)]
+  unsigned char* qbuf;    // [kItemBufs][kblocks][NQ * 128 bytes] (not WIDE)
   unsigned char* meta;    // [kMetaBufs][kMetaBytes] row norms
-  float* thr_s;           // [kItemBufs][kTcNQ] filter thresholds
-  int* qi_s;              // [kItemBufs][kTcNQ] query indices (-1 unused)
+  float* thr_s;           // [kItemBufs][NQ] filter thresholds
+  int* qi_s;              // [kItemBufs][NQ] query indices (-1 unused)
   TcItem* itm;            // [kItemBufs]
   int* wq_row;            // [kFilterWarps][kQueueCap] survivor queues: row of x_sorted
   int* wq_meta;           // [kFilterWarps][kQueueCap] (item slot << 8) | query j
@@ -134,28 +141,28 @@ struct SmemLayout {
   uint64_t* empty_bar;    // [kMaxSlots]
   uint64_t* q_full;       // [kItemBufs]
   uint64_t* q_empty;      // [kItemBufs]
-  uint64_t* acc_full;     // [kAccSets]
-  uint64_t* acc_empty;    // [kAccSets]
+  uint64_t* acc_full;     // [kMaxAccSets]
+  uint64_t* acc_empty;    // [kMaxAccSets]
   uint64_t* meta_full;    // [kMetaBufs]
   uint64_t* meta_empty;   // [kMetaBufs]
   uint32_t* tmem_slot;
 };
 
-__host__ __device__ inline size_t smem_fixed_bytes(int kblocks) {
-  return (size_t)kItemBufs * kblocks * kQBoxBytes + (size_t)kMetaBufs * kMetaBytes +
-         2 * kItemBufs * kTcNQ * sizeof(float) + kItemBufs * sizeof(TcItem) +
+__host__ __device__ inline size_t smem_fixed_bytes(int kblocks, bool wide, int nq) {
+  return (wide ? 0 : (size_t)kItemBufs * kblocks * nq * 128) + (size_t)kMetaBufs * kMetaBytes +
+         2 * kItemBufs * nq * sizeof(float) + kItemBufs * sizeof(TcItem) +
          2 * kFilterWarps * kQueueCap * sizeof(int) +
-         (2 * kMaxSlots + 2 * kItemBufs + 2 * kAccSets + 2 * kMetaBufs) * sizeof(uint64_t) + 16;
+         (2 * kMaxSlots + 2 * kItemBufs + 2 * kMaxAccSets + 2 * kMetaBufs) * sizeof(uint64_t) + 16;
 }
 
-__device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int n_slots, int kblocks) {
+__device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int n_slots, int kblocks, bool wide, int nq) {
   SmemLayout s;
   s.slots = base;
-  s.qbuf = s.slots + (size_t)n_slots * kSlotBytes;
-  s.meta = s.qbuf + (size_t)kItemBufs * kblocks * kQBoxBytes;
+  s.qbuf = s.slots + (size_t)n_slots * (kSlotBytes + (wide ? nq * 128u : 0u));
+  s.meta = s.qbuf + (wide ? 0 : (size_t)kItemBufs * kblocks * nq * 128);
   s.thr_s = reinterpret_cast<float*>(s.meta + (size_t)kMetaBufs * kMetaBytes);
-  s.qi_s = reinterpret_cast<int*>(s.thr_s + kItemBufs * kTcNQ);
-  s.itm = reinterpret_cast<TcItem*>(s.qi_s + kItemBufs * kTcNQ);
+  s.qi_s = reinterpret_cast<int*>(s.thr_s + kItemBufs * nq);
+  s.itm = reinterpret_cast<TcItem*>(s.qi_s + kItemBufs * nq);
   s.wq_row = reinterpret_cast<int*>(s.itm + kItemBufs);
   s.wq_meta = s.wq_row + kFilterWarps * kQueueCap;
   s.full_bar = reinterpret_cast<uint64_t*>(s.wq_meta + kFilterWarps * kQueueCap);
@@ -163,23 +170,26 @@ __device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int n_slot
   s.q_full = s.empty_bar + kMaxSlots;
   s.q_empty = s.q_full + kItemBufs;
   s.acc_full = s.q_empty + kItemBufs;
-  s.acc_empty = s.acc_full + kAccSets;
-  s.meta_full = s.acc_empty + kAccSets;
+  s.acc_empty = s.acc_full + kMaxAccSets;
+  s.meta_full = s.acc_empty + kMaxAccSets;
   s.meta_empty = s.meta_full + kMetaBufs;
   s.tmem_slot = reinterpret_cast<uint32_t*>(s.meta_empty + kMetaBufs);
   return s;
 }
 
 // What the producer knows about an item it has not published yet (one pipeline stage per field group).
+template <int CH>
 struct Ahead {
-  TcItem rec;   // warp-uniform
-  int qi;       // lane j: query index of the item's pair j (-1 past nq)
-  float qn2;    // lane j: |q|^2
+  TcItem rec;     // warp-uniform
+  int qi[CH];     // lane l, chunk c: query index of the item's pair 32 c + l (-1 past nq)
+  float qn2[CH];  // |q|^2 of that query
 };
 
 // Scores the first n (<= 32) entries of a warp's survivor queue, one per lane, and appends the
 // candidates within their query's bound to its buffer.  Returns nothing; the caller advances the queue.
-template <int METRIC>
+// Queue entry: the row of x_sorted and, QGLOBAL, the pair index (query vector = qs[pair], query index =
+// pq[pair]) or else (item slot << 8) | query j of the item whose queries are in shared memory.
+template <int METRIC, bool QGLOBAL>
 __device__ __forceinline__ void score_batch(const TcScanArgs& a, const SmemLayout& s, int kblocks,
                                             const int* q_row, const int* q_meta, unsigned head, int n,
                                             int lane, unsigned& n_appended) {
@@ -187,16 +197,25 @@ __device__ __forceinline__ void score_batch(const TcScanArgs& a, const SmemLayou
     const unsigned e = (head + (unsigned)lane) & (kQueueCap - 1);
     const int row = q_row[e];
     const int meta = q_meta[e];
-    const int islot = meta >> 8, j = meta & 255;
-    TcQueryShared q;
-    q.base = s.qbuf + (size_t)islot * kblocks * kQBoxBytes + j * 128;
-    q.sw = j & 7;
-    // the bound is read fresh: other items of the same query may have lowered it since this item was
-    // picked up (the loads below are independent of the row loads and overlap them)
-    const int qi = s.qi_s[islot * kTcNQ + j];
-    const float ext = __ldcg(a.tau_g + qi);
     const int id = __ldg(a.ids + row);
-    const float dist = tc_thread_distance<METRIC, 16>(a.xs + (size_t)row * a.d_pad, q, a.d);
+    int qi;
+    float dist;
+    if (QGLOBAL) {
+      qi = __ldg(a.pq + meta);
+      TcQueryGlobal q;
+      q.q = a.qs + (size_t)meta * a.d_pad;
+      dist = tc_thread_distance<METRIC, 16>(a.xs + (size_t)row * a.d_pad, q, a.d);
+    } else {
+      const int islot = meta >> 8, j = meta & 255;
+      qi = s.qi_s[islot * kTcNQ + j];
+      TcQueryShared q;
+      q.base = s.qbuf + (size_t)islot * kblocks * kQBoxBytes + j * 128;
+      q.sw = j & 7;
+      dist = tc_thread_distance<METRIC, 16>(a.xs + (size_t)row * a.d_pad, q, a.d);
+    }
+    // the bound is read fresh: other items of the same query may have lowered it since this item was
+    // picked up
+    const float ext = __ldcg(a.tau_g + qi);
     if (dist <= ext) {
       const int pos = atomicAdd(a.cand_n + qi, 1);
       if (pos < a.cap) {
@@ -243,13 +262,20 @@ __device__ __forceinline__ void score_batch(const TcScanArgs& a, const SmemLayou
   __syncwarp();
 }
 
-template <int METRIC>
+template <int METRIC, int NQ, bool WIDE, bool QGLOBAL>
 __global__ void __launch_bounds__(kThreads, 1)
     scan_tc_kernel(const TcScanArgs a, const __grid_constant__ CUtensorMap map_x,
                    const __grid_constant__ CUtensorMap map_x32, const __grid_constant__ CUtensorMap map_q) {
+  static_assert(!WIDE || QGLOBAL, "wide rows: the queries are not resident in shared memory");
+  static_assert(NQ == kTcNQ || (NQ == kTcNQMax && WIDE), "128 queries per item: their K blocks travel with the tiles");
+  constexpr int kCh = NQ / 32;                  // 32-column chunks of the accumulator
+  constexpr int kSets = kTmemCols / NQ;         // TMEM accumulator ring depth
+  static_assert(kSets % kGroups == 0 && kSets >= 2 && kSets <= kMaxAccSets, "accumulator ring");
+  constexpr uint32_t kQBytes = NQ * 128u;       // one K block of the item's queries
   extern __shared__ unsigned char stc_smem_raw[];
   unsigned char* base = stc_smem_raw + ((1024u - (smem_u32(stc_smem_raw) & 1023u)) & 1023u);
-  const SmemLayout s = carve_smem(base, a.n_slots, a.kblocks);
+  const SmemLayout s = carve_smem(base, a.n_slots, a.kblocks, WIDE, NQ);
+  constexpr uint32_t kSlotStride = kSlotBytes + (WIDE ? kQBytes : 0u);  // WIDE: rows + the queries' K block
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -270,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&s.q_full[i], 1);
       mbar_init(&s.q_empty[i], kFilterWarps);
     }
-    for (int i = 0; i < kAccSets; ++i) {
+    for (int i = 0; i < kSets; ++i) {
       mbar_init(&s.acc_full[i], 1);
       mbar_init(&s.acc_empty[i], 4);
     }
@@ -301,17 +327,24 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       return r;
     };
-    auto load_pair = [&](Ahead& h) {
-      h.qi = -1;
-      h.qn2 = 0.f;
-      if (lane < h.rec.nq) {
-        h.qi = __ldg(a.pq + h.rec.pair_base + lane);
-        h.qn2 = __ldg(a.pqn2 + h.rec.pair_base + lane);
+    auto load_pair = [&](Ahead<kCh>& h) {
+#pragma unroll
+      for (int c = 0; c < kCh; ++c) {
+        h.qi[c] = -1;
+        h.qn2[c] = 0.f;
+        if (32 * c + lane < h.rec.nq) {
+          h.qi[c] = __ldg(a.pq + h.rec.pair_base + 32 * c + lane);
+          h.qn2[c] = __ldg(a.pqn2 + h.rec.pair_base + 32 * c + lane);
+        }
       }
+    };
+    auto load_tau = [&](const Ahead<kCh>& h, float (&tau)[kCh]) {
+#pragma unroll
+      for (int c = 0; c < kCh; ++c) tau[c] = h.qi[c] >= 0 ? __ldcg(a.tau_g + h.qi[c]) : neg_inf();
     };
     // look-ahead pipeline: index of item i+3, record of i+2, pair state of i+1, tau_g of i
     int idx3 = next_index();
-    Ahead cur, nx1, nx2;
+    Ahead<kCh> cur, nx1, nx2;
     cur.rec = load_rec(idx3);
     idx3 = next_index();
     nx1.rec = load_rec(idx3);
@@ -320,14 +353,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     idx3 = next_index();
     load_pair(cur);
     load_pair(nx1);
-    float tau_cur = cur.qi >= 0 ? __ldcg(a.tau_g + cur.qi) : neg_inf();
+    float tau_cur[kCh], tau_nx1[kCh];
+    load_tau(cur, tau_cur);
     unsigned ring = 0, icount = 0, tcount = 0;
     while (true) {
       // issue the look-ahead loads first: they complete while this item's tiles are streamed
       const TcItem rec3 = load_rec(idx3);                      // item i+3
       idx3 = next_index();                                     // index of item i+4
       load_pair(nx2);                                          // item i+2 (its record arrived last iteration)
-      const float tau_nx1 = nx1.qi >= 0 ? __ldcg(a.tau_g + nx1.qi) : neg_inf();  // item i+1
+      load_tau(nx1, tau_nx1);                                  // item i+1
 
       const int islot = (int)(icount % kItemBufs);
       MBAR_WAIT(&s.q_empty[islot], ((icount / kItemBufs) & 1u) ^ 1u);
@@ -339,19 +373,24 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         break;
       }
-      {  // lane j: state of the item's query j
+#pragma unroll
+      for (int c = 0; c < kCh; ++c) {  // lane l: state of the item's query 32 c + l
         float th = neg_inf();
-        if (lane < rec.nq) th = make_thr<METRIC>(tau_cur, cur.qn2, a.l2_slack);
-        s.thr_s[islot * kTcNQ + lane] = th;
-        s.qi_s[islot * kTcNQ + lane] = cur.qi;
+        if (32 * c + lane < rec.nq) th = make_thr<METRIC>(tau_cur[c], cur.qn2[c], a.l2_slack);
+        s.thr_s[islot * NQ + 32 * c + lane] = th;
+        s.qi_s[islot * NQ + 32 * c + lane] = cur.qi[c];
       }
       if (lane == 0) s.itm[islot] = rec;
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive_expect_tx(&s.q_full[islot], (unsigned)kblocks * kQBoxBytes);
-        unsigned char* qdst = s.qbuf + (size_t)islot * kblocks * kQBoxBytes;
-        for (int kb = 0; kb < kblocks; ++kb)
-          tma_load_2d(qdst + kb * kQBoxBytes, &map_q, kb * kTcBK, rec.pair_base, &s.q_full[islot]);
+        if (WIDE) {
+          mbar_arrive(&s.q_full[islot]);  // only the item's state: the queries travel with the row tiles
+        } else {
+          mbar_arrive_expect_tx(&s.q_full[islot], (unsigned)kblocks * kQBytes);
+          unsigned char* qdst = s.qbuf + (size_t)islot * kblocks * kQBytes;
+          for (int kb = 0; kb < kblocks; ++kb)
+            tma_load_2d(qdst + kb * kQBytes, &map_q, kb * kTcBK, rec.pair_base, &s.q_full[islot]);
+        }
         const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
         for (int t = 0; t < n_tiles; ++t, ++tcount) {
           const int trow0 = rec.row0 + t * kTile;
@@ -378,30 +417,33 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int kb = 0; kb < kblocks; ++kb, ++ring) {
             const unsigned sl = ring % n_slots;
             MBAR_WAIT(&s.empty_bar[sl], ((ring / n_slots) & 1u) ^ 1u);
-            unsigned char* dst = s.slots + (size_t)sl * kSlotBytes;
+            unsigned char* dst = s.slots + (size_t)sl * kSlotStride;
             // a box is always written in full (rows / columns past the tensor are zero filled)
+            const unsigned qbytes = WIDE ? kQBytes : 0u;
             if (sub == 0) {
-              mbar_arrive_expect_tx(&s.full_bar[sl], kSlotBytes);
+              mbar_arrive_expect_tx(&s.full_bar[sl], kSlotBytes + qbytes);
               tma_load_2d(dst, &map_x, kb * kTcBK, trow0, &s.full_bar[sl]);
             } else {
-              mbar_arrive_expect_tx(&s.full_bar[sl], (unsigned)sub * kSubBoxBytes);
+              mbar_arrive_expect_tx(&s.full_bar[sl], (unsigned)sub * kSubBoxBytes + qbytes);
               for (int b = 0; b < sub; ++b)
                 tma_load_2d(dst + b * kSubBoxBytes, &map_x32, kb * kTcBK, trow0 + 32 * b, &s.full_bar[sl]);
             }
+            if (WIDE) tma_load_2d(dst + kSlotBytes, &map_q, kb * kTcBK, rec.pair_base, &s.full_bar[sl]);
           }
         }
       }
       __syncwarp();
       ++icount;
       cur = nx1;
-      tau_cur = tau_nx1;
+#pragma unroll
+      for (int c = 0; c < kCh; ++c) tau_cur[c] = tau_nx1[c];
       nx1 = nx2;
       nx2.rec = rec3;
     }
   } else if (warp == 1) {
     // =================================== MMA issuer =======================================
     if (lane == 0) {
-      const uint32_t idesc = make_tf32_idesc(kTcNQ);
+      const uint32_t idesc = make_tf32_idesc(NQ);
       unsigned ring = 0, icount = 0, tcount = 0;
       while (true) {
         const int islot = (int)(icount % kItemBufs);
@@ -409,18 +451,19 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int nq = s.itm[islot].nq;
         if (nq == 0) break;
         const int n_tiles = (s.itm[islot].row1 - s.itm[islot].row0 + kTile - 1) / kTile;
-        const unsigned char* qsrc = s.qbuf + (size_t)islot * kblocks * kQBoxBytes;
+        const unsigned char* qsrc = s.qbuf + (size_t)islot * kblocks * kQBytes;
         for (int t = 0; t < n_tiles; ++t, ++tcount) {
-          const unsigned set = tcount % kAccSets;
-          MBAR_WAIT(&s.acc_empty[set], ((tcount / kAccSets) & 1u) ^ 1u);  // the filter drained this set
+          const unsigned set = tcount % kSets;
+          MBAR_WAIT(&s.acc_empty[set], ((tcount / kSets) & 1u) ^ 1u);  // the filter drained this set
           tc_fence_after();
-          const uint32_t acc = tmem_base + set * (uint32_t)kTcNQ;
+          const uint32_t acc = tmem_base + set * (uint32_t)NQ;
           for (int kb = 0; kb < kblocks; ++kb, ++ring) {
             const unsigned sl = ring % n_slots;
             MBAR_WAIT(&s.full_bar[sl], (ring / n_slots) & 1u);
             tc_fence_after();
-            const uint64_t da = make_kmajor_sw128_desc(s.slots + (size_t)sl * kSlotBytes);
-            const uint64_t db = make_kmajor_sw128_desc(qsrc + kb * kQBoxBytes);
+            const unsigned char* slot = s.slots + (size_t)sl * kSlotStride;
+            const uint64_t da = make_kmajor_sw128_desc(slot);
+            const uint64_t db = make_kmajor_sw128_desc(WIDE ? slot + kSlotBytes : qsrc + kb * kQBytes);
 #pragma unroll
             for (int k8 = 0; k8 < kTcBK / 8; ++k8)  // UMMA K = 8 tf32 = 32 bytes: +2 in (addr >> 4)
               tc_mma_tf32(acc, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc,
@@ -451,8 +494,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       MBAR_WAIT(&s.q_full[islot], (icount / kItemBufs) & 1u);
       const TcItem rec = s.itm[islot];
       if (rec.nq == 0) break;
-      const float* th = s.thr_s + islot * kTcNQ;
+      const float* th = s.thr_s + islot * NQ;
       const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
+      const int n_ch = (rec.nq + 31) >> 5;  // column chunks that hold queries
       for (int t = 0; t < n_tiles; ++t, ++tcount) {
         if ((int)(tcount % kGroups) != group) continue;
         const int row = rec.row0 + t * kTile + r_local;
@@ -463,16 +507,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (row >= (a.n_rows & ~3ll)) xn = valid ? a.xnorm[row] : 0.f;
         __syncwarp();
         if (lane == 0) mbar_arrive(&s.meta_empty[mb]);
-        const unsigned set = tcount % kAccSets;
-        MBAR_WAIT(&s.acc_full[set], (tcount / kAccSets) & 1u);
-        tc_fence_after();
-        uint32_t v0[16], v1[16];
-        tc_ld16_nowait(lane_base + set * (uint32_t)kTcNQ, v0);
-        tc_ld16_nowait(lane_base + set * (uint32_t)kTcNQ + 16u, v1);
-        tc_wait_ld2(v0, v1);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.acc_empty[set]);  // TMEM set free for the tile kAccSets ahead
         float ra, rb;  // bound = ra * dot + rb
         if (METRIC == NLSH_METRIC_L2) {
           ra = -2.0f;
@@ -481,48 +515,70 @@ __global__ void __launch_bounds__(kThreads, 1)
           ra = -1.0f / fmaxf(sqrtf(xn), 1e-8f);
           rb = 0.f;
         }
-        unsigned mask = 0;
+        const unsigned set = tcount % kSets;
+        MBAR_WAIT(&s.acc_full[set], (tcount / kSets) & 1u);
+        tc_fence_after();
+        unsigned masks[kCh];
 #pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          const float4 t0 = *reinterpret_cast<const float4*>(th + j4);
-          const float4 t1 = *reinterpret_cast<const float4*>(th + 16 + j4);
-          mask |= (fmaf(ra, __uint_as_float(v0[j4 + 0]), rb) <= t0.x ? 1u : 0u) << (j4 + 0);
-          mask |= (fmaf(ra, __uint_as_float(v0[j4 + 1]), rb) <= t0.y ? 1u : 0u) << (j4 + 1);
-          mask |= (fmaf(ra, __uint_as_float(v0[j4 + 2]), rb) <= t0.z ? 1u : 0u) << (j4 + 2);
-          mask |= (fmaf(ra, __uint_as_float(v0[j4 + 3]), rb) <= t0.w ? 1u : 0u) << (j4 + 3);
-          mask |= (fmaf(ra, __uint_as_float(v1[j4 + 0]), rb) <= t1.x ? 1u : 0u) << (16 + j4 + 0);
-          mask |= (fmaf(ra, __uint_as_float(v1[j4 + 1]), rb) <= t1.y ? 1u : 0u) << (16 + j4 + 1);
-          mask |= (fmaf(ra, __uint_as_float(v1[j4 + 2]), rb) <= t1.z ? 1u : 0u) << (16 + j4 + 2);
-          mask |= (fmaf(ra, __uint_as_float(v1[j4 + 3]), rb) <= t1.w ? 1u : 0u) << (16 + j4 + 3);
-        }
-        if (!valid) mask = 0;
-        // queue this warp's survivors, one per lane and round; a full batch is scored right away
-        while (true) {
-          const bool has = mask != 0;
-          const unsigned b = __ballot_sync(NLSH_FULL_MASK, has);
-          if (b == 0) break;
-          if (has) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const unsigned e = (head + (unsigned)count + __popc(b & ((1u << lane) - 1u))) & (kQueueCap - 1);
-            q_row[e] = row;
-            q_meta[e] = (islot << 8) | j;
+        for (int c = 0; c < kCh; ++c) {
+          masks[c] = 0;
+          if (c < n_ch) {  // warp-uniform
+            uint32_t v0[16], v1[16];
+            tc_ld16_nowait(lane_base + set * (uint32_t)NQ + 32u * c, v0);
+            tc_ld16_nowait(lane_base + set * (uint32_t)NQ + 32u * c + 16u, v1);
+            tc_wait_ld2(v0, v1);
+            unsigned mask = 0;
+#pragma unroll
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+              const float4 t0 = *reinterpret_cast<const float4*>(th + 32 * c + j4);
+              const float4 t1 = *reinterpret_cast<const float4*>(th + 32 * c + 16 + j4);
+              mask |= (fmaf(ra, __uint_as_float(v0[j4 + 0]), rb) <= t0.x ? 1u : 0u) << (j4 + 0);
+              mask |= (fmaf(ra, __uint_as_float(v0[j4 + 1]), rb) <= t0.y ? 1u : 0u) << (j4 + 1);
+              mask |= (fmaf(ra, __uint_as_float(v0[j4 + 2]), rb) <= t0.z ? 1u : 0u) << (j4 + 2);
+              mask |= (fmaf(ra, __uint_as_float(v0[j4 + 3]), rb) <= t0.w ? 1u : 0u) << (j4 + 3);
+              mask |= (fmaf(ra, __uint_as_float(v1[j4 + 0]), rb) <= t1.x ? 1u : 0u) << (16 + j4 + 0);
+              mask |= (fmaf(ra, __uint_as_float(v1[j4 + 1]), rb) <= t1.y ? 1u : 0u) << (16 + j4 + 1);
+              mask |= (fmaf(ra, __uint_as_float(v1[j4 + 2]), rb) <= t1.z ? 1u : 0u) << (16 + j4 + 2);
+              mask |= (fmaf(ra, __uint_as_float(v1[j4 + 3]), rb) <= t1.w ? 1u : 0u) << (16 + j4 + 3);
+            }
+            masks[c] = valid ? mask : 0u;
           }
-          const int added = __popc(b);
-          count += added;
-          n_surv += (unsigned)added;
-          __syncwarp();
-          if (count >= 32) {
-            score_batch<METRIC>(a, s, kblocks, q_row, q_meta, head, 32, lane, n_appended);
-            head = (head + 32u) & (kQueueCap - 1);
-            count -= 32;
-            ++n_batches;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.acc_empty[set]);  // TMEM set free for the tile kSets ahead
+        // queue this warp's survivors, one per lane and round; a full batch is scored right away
+#pragma unroll
+        for (int c = 0; c < kCh; ++c) {
+          unsigned mask = masks[c];
+          while (true) {
+            const bool has = mask != 0;
+            const unsigned b = __ballot_sync(NLSH_FULL_MASK, has);
+            if (b == 0) break;
+            if (has) {
+              const int j = 32 * c + __ffs(mask) - 1;
+              mask &= mask - 1;
+              const unsigned e = (head + (unsigned)count + __popc(b & ((1u << lane) - 1u))) & (kQueueCap - 1);
+              q_row[e] = row;
+              q_meta[e] = QGLOBAL ? rec.pair_base + j : ((islot << 8) | j);
+            }
+            const int added = __popc(b);
+            count += added;
+            n_surv += (unsigned)added;
+            __syncwarp();
+            if (count >= 32) {
+              score_batch<METRIC, QGLOBAL>(a, s, kblocks, q_row, q_meta, head, 32, lane, n_appended);
+              head = (head + 32u) & (kQueueCap - 1);
+              count -= 32;
+              ++n_batches;
+            }
           }
         }
       }
       // the item's queries leave shared memory with this arrive: score what is still queued
-      if (count > 0) {
-        score_batch<METRIC>(a, s, kblocks, q_row, q_meta, head, count, lane, n_appended);
+      // (QGLOBAL entries do not refer to the item slot and stay queued across items)
+      if (!QGLOBAL && count > 0) {
+        score_batch<METRIC, QGLOBAL>(a, s, kblocks, q_row, q_meta, head, count, lane, n_appended);
         head = (head + (unsigned)count) & (kQueueCap - 1);
         count = 0;
         ++n_flush;
@@ -530,6 +586,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.q_empty[islot]);
       ++icount;
+    }
+    if (QGLOBAL && count > 0) {
+      score_batch<METRIC, QGLOBAL>(a, s, kblocks, q_row, q_meta, head, count, lane, n_appended);
+      ++n_flush;
     }
     if (a.stats != nullptr) {
       // debug counters: [0] survivors of the filter, [1] full batches, [2] end-of-item batches,
@@ -707,14 +767,67 @@ __global__ void __launch_bounds__(128, 5)
   }
 }
 
-size_t scan_tc_smem(int kblocks, int n_slots) {
-  return (size_t)n_slots * kSlotBytes + smem_fixed_bytes(kblocks) + 1024;
+// The same seed for wide rows (d_pad > 128) or k > 32: one warp per query, one sample row per lane and
+// step, every distance by one thread in the scorer's own arithmetic (tc_thread_distance), lists of up to
+// 128 entries.  The rows of a step are 32 different rows, so this kernel is latency bound; it only runs
+// where the pipelined 8-lanes-per-row kernel above does not apply.
+template <int METRIC, int KPL>
+__global__ void __launch_bounds__(128)
+    seed_tau_generic_kernel(const float* __restrict__ qn, const int* __restrict__ probes,
+                            const int* __restrict__ offsets, const float* __restrict__ xs, int n_buckets, int p,
+                            int d, int d_pad, int k, int seed_rows, int seed_div, long long n_queries,
+                            float* __restrict__ tau_g, float* __restrict__ tau0) {
+  const long long q = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= n_queries) return;
+  const int lane = lane_id();
+  TcQueryGlobal qg;
+  qg.q = qn + (size_t)q * d_pad;
+  WarpTopK<KPL, int> top;
+  top.init(NLSH_ID_SENTINEL);
+  int budget = -1, taken = 0;
+  for (int j = 0; j < p && budget != 0; ++j) {  // warp-uniform
+    const int b = probes[q * p + j];
+    if (b < 0 || b >= n_buckets) continue;
+    bool dup = false;
+    for (int e = 0; e < j; ++e) dup |= probes[q * p + e] == b;
+    if (dup) continue;
+    const int r0 = offsets[b];
+    const int size = offsets[b + 1] - r0;
+    if (size <= 0) continue;
+    if (budget < 0) {
+      budget = seed_rows;
+      const int want = size / seed_div;
+      if (want > budget) budget = want;
+      if (budget > kMaxSeedRows) budget = kMaxSeedRows;
+    }
+    const int n = size < budget ? size : budget;
+    for (int base = 0; base < n; base += 32) {
+      const int r = base + lane;
+      float dist = 0.f;
+      if (r < n) dist = tc_thread_distance<METRIC, 8>(xs + (size_t)(r0 + r) * d_pad, qg, d);
+      top.offer(dist, taken + r, r < n, k);
+    }
+    budget -= n;
+    taken += n;
+  }
+  if (lane == 0) {
+    float t = pos_inf();
+    // same arithmetic as the scorer: no inflation is needed, but the bound must not be below a distance
+    // the scorer would compute for the same row, which it is not (identical operations)
+    if (taken >= k && top.tau < pos_inf()) t = top.tau;
+    tau_g[q] = t;
+    tau0[q] = t;
+  }
+}
+
+size_t scan_tc_smem(int kblocks, int n_slots, bool wide, int nq) {
+  return (size_t)n_slots * (kSlotBytes + (wide ? nq * 128u : 0u)) + smem_fixed_bytes(kblocks, wide, nq) + 1024;
 }
 
 }  // namespace
 
 bool nlsh_scan_tc_supported(int d, int k, int metric) {
-  return d >= 1 && (d + 3) / 4 * 4 <= kMaxKBlocks * kTcBK && k <= 32 &&
+  return d >= 1 && (d + 3) / 4 * 4 <= kMaxWideKBlocks * kTcBK && k >= 1 && k <= NLSH_MAX_K &&
          (metric == NLSH_METRIC_L2 || metric == NLSH_METRIC_ANGULAR);
 }
 
@@ -729,17 +842,16 @@ int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, 
   gather_pair_queries_kernel<<<(unsigned)blocks, 256, 0, st>>>(qn, pairs, n_valid, n_pairs, p, d_pad, qs, pq,
                                                              pqn2);
   NLSH_CUDA_TRY(nlsh_post_launch());
-  // Sample rows per query: 32 .. 384 by the average bucket size (measured in round 1 with 10k queries,
-  // p = 8: 305-row buckets 192 rows, 2441-row buckets 384 rows), and at least 1/seed_div of the query's
-  // own first bucket, so that the rows of a large bucket that fall below the bound stay a few dozen.
+  // Sample rows per query: half the average bucket, 32 .. 128, and at least 1/seed_div of the query's own
+  // first bucket (2441-row buckets: 152 rows), so that the rows of a large bucket that fall below the bound
+  // stay a few dozen.  The scan's time hardly depends on the survivors (config 4: 1.08 M survivors 0.96 ms,
+  // 2.47 M 1.03 ms) while the sample costs 0.55 us per row and batch: 152 rows 1.25 ms per call, 384 rows
+  // 1.32 ms; on an 8-GPU shard 128 .. 192 rows are equal, 64 rows lose (profiles/r2_experiments).
   // NLSH_SCAN_SEED=<rows> overrides the base sample; the scan needs the seed (every tau_g is written here).
   const long long avg = n_buckets > 0 ? n_rows / n_buckets : 0;
   int seed_rows = (int)(avg / 2 / 32 * 32);
   if (seed_rows < 32) seed_rows = 32;
   if (seed_rows > 128) seed_rows = 128;
-  if (avg >= 256) seed_rows = 192;
-  if (avg >= 1024) seed_rows = 256;
-  if (avg >= 2048) seed_rows = 384;
   if (const char* env = getenv("NLSH_SCAN_SEED")) seed_rows = atoi(env);
   if (seed_rows < 0) seed_rows = 0;  // 0: no sample, tau_g = +inf (every row is scored; A/B and tests only)
   if (seed_rows > kMaxSeedRows) seed_rows = kMaxSeedRows;
@@ -747,47 +859,79 @@ int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, 
   if (const char* env = getenv("NLSH_SCAN_SEED_DIV")) seed_div = atoi(env);
   if (seed_div < 1) seed_div = 1;
   if (seed_rows == 0) seed_div = 1 << 30;
+  if (seed_rows > 0 && seed_rows < 4 * k) seed_rows = 4 * k;  // a sample of at least a few times k rows
   const unsigned sb = (unsigned)((n_queries + 3) / 4);
-  if (metric == NLSH_METRIC_L2)
-    seed_tau_kernel<NLSH_METRIC_L2><<<sb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad, k,
-                                                       seed_rows, seed_div, n_queries, tau_g, tau0);
-  else
-    seed_tau_kernel<NLSH_METRIC_ANGULAR><<<sb, 128, 0, st>>>(qn, probes, offsets, xs, n_buckets, p, d, d_pad, k,
-                                                            seed_rows, seed_div, n_queries, tau_g, tau0);
+#define NLSH_SEED_ARGS qn, probes, offsets, xs, n_buckets, p, d, d_pad, k, seed_rows, seed_div, n_queries, tau_g, tau0
+  if (d_pad <= kMaxKBlocks * kTcBK && k <= 32) {
+    if (metric == NLSH_METRIC_L2)
+      seed_tau_kernel<NLSH_METRIC_L2><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
+    else
+      seed_tau_kernel<NLSH_METRIC_ANGULAR><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
+  } else if (metric == NLSH_METRIC_L2) {
+    if (k <= 32) seed_tau_generic_kernel<NLSH_METRIC_L2, 1><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
+    else if (k <= 64) seed_tau_generic_kernel<NLSH_METRIC_L2, 2><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
+    else seed_tau_generic_kernel<NLSH_METRIC_L2, 4><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
+  } else {
+    if (k <= 32) seed_tau_generic_kernel<NLSH_METRIC_ANGULAR, 1><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
+    else if (k <= 64) seed_tau_generic_kernel<NLSH_METRIC_ANGULAR, 2><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
+    else seed_tau_generic_kernel<NLSH_METRIC_ANGULAR, 4><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
+  }
+#undef NLSH_SEED_ARGS
   return nlsh_check_cuda(nlsh_post_launch(), "seed_tau_kernel launch");
 }
+
+namespace {
+template <int METRIC, int NQ, bool WIDE, bool QGLOBAL>
+int launch_variant(const TcScanArgs& a, const CUtensorMap& map_x, const CUtensorMap& map_x32,
+                   const CUtensorMap& map_q, int grid, size_t smem, cudaStream_t st) {
+  auto kern = scan_tc_kernel<METRIC, NQ, WIDE, QGLOBAL>;
+  NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kThreads, smem, st>>>(a, map_x, map_x32, map_q);
+  return nlsh_check_cuda(nlsh_post_launch(), "scan_tc_kernel launch");
+}
+
+template <int METRIC>
+int launch_metric(const TcScanArgs& a, const CUtensorMap& map_x, const CUtensorMap& map_x32,
+                  const CUtensorMap& map_q, bool wide, bool qglobal, int grid, size_t smem, cudaStream_t st) {
+  if (a.nq_group == kTcNQMax) return launch_variant<METRIC, kTcNQMax, true, true>(a, map_x, map_x32, map_q, grid, smem, st);
+  if (wide) return launch_variant<METRIC, kTcNQ, true, true>(a, map_x, map_x32, map_q, grid, smem, st);
+  if (qglobal) return launch_variant<METRIC, kTcNQ, false, true>(a, map_x, map_x32, map_q, grid, smem, st);
+  return launch_variant<METRIC, kTcNQ, false, false>(a, map_x, map_x32, map_q, grid, smem, st);
+}
+}  // namespace
 
 int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {
   a.kblocks = (a.d_pad + kTcBK - 1) / kTcBK;
   a.l2_slack = 2.1e-6f * sqrtf((float)a.d);
+  if (a.nq_group != kTcNQMax) a.nq_group = kTcNQ;
+  // wide rows, or 128 queries per item: the queries' K blocks travel with the row tiles
+  const bool wide = a.kblocks > kMaxKBlocks || a.nq_group == kTcNQMax;
+  // Scorer query source: the item's shared-memory copy, or (QGLOBAL) the pair-ordered global copy, which
+  // spares the partial batch every warp scores at the end of every item - worth it when items are short
+  // (a few tiles per bucket).  NLSH_TC_QGLOBAL=0/1 overrides (A/B runs).
+  bool qglobal = wide || a.avg_item_rows < 4 * kTile;
+  if (const char* env = getenv("NLSH_TC_QGLOBAL")) qglobal = wide || atoi(env) != 0;
   int n_slots = kMaxSlots;
   // each K block's slot is freed by its own tcgen05.commit, so any ring depth >= 2 makes progress
-  while (n_slots > 3 && scan_tc_smem(a.kblocks, n_slots) > 224 * 1024) --n_slots;
+  while (n_slots > 3 && scan_tc_smem(a.kblocks, n_slots, wide, a.nq_group) > 224 * 1024) --n_slots;
   if (const char* env = getenv("NLSH_TC_SLOTS")) {  // A/B runs
     const int v = atoi(env);
     if (v >= 3 && v < n_slots) n_slots = v;
   }
   a.n_slots = n_slots;
-  const size_t smem = scan_tc_smem(a.kblocks, n_slots);
+  const size_t smem = scan_tc_smem(a.kblocks, n_slots, wide, a.nq_group);
   CUtensorMap map_x, map_x32, map_q;
   int rc;
   if ((rc = tc_make_map(&map_x, a.xs, a.n_rows, a.d_pad, kTile)) != NLSH_OK) return rc;
   if ((rc = tc_make_map(&map_x32, a.xs, a.n_rows, a.d_pad, 32)) != NLSH_OK) return rc;
-  if ((rc = tc_make_map(&map_q, a.qs, a.n_pairs, a.d_pad, kTcNQ)) != NLSH_OK) return rc;
+  if ((rc = tc_make_map(&map_q, a.qs, a.n_pairs, a.d_pad, a.nq_group)) != NLSH_OK) return rc;
   // One persistent CTA per SM; `sm_reserve` SMs are left to other streams (the launch-bound front part of
   // the next batch in nlsh.parallel.PipelinedSearch).  NLSH_TC_GRID=<CTAs> overrides (A/B runs).
   int grid = nlsh_num_sms() - a.sm_reserve;
   if (const char* env = getenv("NLSH_TC_GRID")) grid = atoi(env);
   if (grid < 1) grid = 1;
   if (grid > nlsh_num_sms()) grid = nlsh_num_sms();
-  if (metric == NLSH_METRIC_L2) {
-    auto kern = scan_tc_kernel<NLSH_METRIC_L2>;
-    NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(a, map_x, map_x32, map_q);
-  } else {
-    auto kern = scan_tc_kernel<NLSH_METRIC_ANGULAR>;
-    NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(a, map_x, map_x32, map_q);
-  }
-  return nlsh_check_cuda(nlsh_post_launch(), "scan_tc_kernel launch");
+  if (metric == NLSH_METRIC_L2)
+    return launch_metric<NLSH_METRIC_L2>(a, map_x, map_x32, map_q, wide, qglobal, grid, smem, st);
+  return launch_metric<NLSH_METRIC_ANGULAR>(a, map_x, map_x32, map_q, wide, qglobal, grid, smem, st);
 }

@@ -2,7 +2,8 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int kTcNQ = 32;      // queries per item = UMMA N of the filter GEMM
+constexpr int kTcNQ = 32;      // queries per item = UMMA N of the filter GEMM ...
+constexpr int kTcNQMax = 128;  // ... or 128 when a bucket is probed by 64 or more queries of the batch
 constexpr int kTcLadder = 16;  // threshold-ladder levels per query (scan_tc.cu, "threshold ladder")
 constexpr int kTcLadderDen = 32;  // level l stands for the bound tau0 * (1 - l / kTcLadderDen)
 
@@ -12,7 +13,7 @@ constexpr int kTcLadderDen = 32;  // level l stands for the bound tau0 * (1 - l 
 struct __align__(16) TcItem {
   int row0, row1;  // rows of x_sorted
   int pair_base;
-  int nq;          // 1..kTcNQ; 0 = end-of-work sentinel
+  int nq;          // 1..group size (kTcNQ or kTcNQMax); 0 = end-of-work sentinel
   int chunk;       // chunk index inside the bucket
   int pad[3];
 };
@@ -28,7 +29,7 @@ struct TcScanArgs {
   const float* xs;       // [n_rows, d_pad] bucket-contiguous vectors
   const float* xnorm;    // [n_rows] |x|^2 of each row of xs
   const int* ids;        // [n_rows] vector id of each row of xs
-  const float* qs;       // [n_pairs (+ kTcNQ), d_pad] query vectors in pair order (pre-normalised for ANGULAR)
+  const float* qs;       // [n_pairs (+ kTcNQMax), d_pad] query vectors in pair order (pre-normalised for ANGULAR)
   const int* pq;         // [n_pairs] query index of each pair
   const float* pqn2;     // [n_pairs] |q|^2 of each pair's query
   const TcItem* items;
@@ -45,6 +46,8 @@ struct TcScanArgs {
   long long n_rows;
   long long n_pairs;
   int k, d, d_pad, kblocks, n_slots;
+  int nq_group;          // queries per item: kTcNQ or kTcNQMax (the plan's group size)
+  int avg_item_rows;     // average rows per bucket (chooses the scorer's query source)
   int sm_reserve;        // SMs the persistent grid leaves free (flags bits 8-15 of nlsh_query_scan_topk)
   float l2_slack;        // 2.1e-6 * sqrt(d): bound of the eps cross term of F.pairwise_distance
 };

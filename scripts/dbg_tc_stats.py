@@ -15,7 +15,7 @@ idx = Indexer(hashing, X, hashing.distance, metric=metric)
 for rows in (128, 256):
     os.environ["NLSH_SCAN_SEED"] = str(rows)
     ids, dd, nc = idx.query_tensors(Q, k=k, hash_times=p); torch.cuda.synchronize()
-    ws = list(_native._workspaces.values())[0]
+    ws = list(_native._workspaces.values())[0].buf
     B = 1 << hs
     st = ws.view(torch.uint8)[(2 * B + 2) * 4:(2 * B + 2) * 4 + 18 * 8].view(torch.int64).cpu().tolist()
     pairs = int(nc.long().sum())

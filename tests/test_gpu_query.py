@@ -126,6 +126,10 @@ def test_query_against_oracle(oracle, n, d, hs, nq, p, k, metric):
     (30001, 128, 5, 600, 3, 10, "l2", "mixture"),        # row count not a multiple of 4: the last rows' norms
     (9999, 64, 3, 500, 2, 10, "angular", "mixture"),     # are read outside the 16-byte aligned bulk copies
     (777, 16, 1, 300, 2, 32, "l2", "mixture"),           # two buckets of a few tiles, k = 32
+    (20_000, 960, 5, 300, 3, 100, "l2", "mixture"),      # config-5 shape: wide rows (queries ride with the row
+    (20_000, 200, 5, 300, 3, 10, "angular", "mixture"),  # tiles' K blocks), k up to 128
+    (20_000, 132, 4, 200, 2, 50, "l2", "mixture"),       # a last K block of 4 columns
+    (9000, 520, 3, 150, 2, 128, "l2", "duplicates"),
 ])
 def test_tensor_core_filter_is_exact(monkeypatch, n, d, hs, nq, p, k, metric, kind):
     """scan_tc.cu (tcgen05 tf32 GEMM as a filter + exact re-rank) must return bit-for-bit what the
@@ -155,8 +159,11 @@ def test_tensor_core_filter_is_exact(monkeypatch, n, d, hs, nq, p, k, metric, ki
     assert (ids[:, 0] >= 0).all()
     # the same through the filter's other regimes: candidate buffers of k entries (almost every query
     # overflows and is re-scanned exactly in the merge), no threshold ladder (seed bound only), no seed
-    # (bound +inf: every row is scored)
-    for flags, env in ((4, {}), (0, {"NLSH_TC_LADDER": "0"}), (0, {"NLSH_SCAN_SEED": "0"})):
+    # (bound +inf: every row is scored), the scorer's query from global / shared memory, 16 SMs left free,
+    # 128 / 32 queries per item
+    for flags, env in ((4, {}), (0, {"NLSH_TC_LADDER": "0"}), (0, {"NLSH_SCAN_SEED": "0"}),
+                       (0, {"NLSH_TC_QGLOBAL": "1"}), (0, {"NLSH_TC_QGLOBAL": "0"}), (16 << 8, {}),
+                       (0, {"NLSH_TC_NQ": "128"}), (0, {"NLSH_TC_NQ": "32"})):
         if env.get("NLSH_SCAN_SEED") == "0" and n * nq * p > 2e9:
             continue  # scoring every pair one thread at a time is only for the small cases
         for name, val in env.items():
