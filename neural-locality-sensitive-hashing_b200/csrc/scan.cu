@@ -1310,13 +1310,13 @@ bool scan_batch_prefers_tc(int64_t n_queries, int32_t p, int32_t n_buckets) {
 }  // namespace
 
 namespace {
-// Queries per item of the tensor-core scan: 128 when the batch puts 64 or more (query, probe) pairs on a
-// probed bucket (configs 1, 2, 5: a row tile then serves 128 queries per pass instead of 32), else 32.
-// NLSH_TC_NQ=32/128 overrides (A/B runs).
-int tc_group_size(int64_t n_queries, int32_t p, int32_t n_buckets) {
+// Queries per item of the tensor-core scan: 128 for wide rows (d > 128) when the batch puts 64 or more
+// (query, probe) pairs on a probed bucket (config 5: 6.3 against 7.0 ms), else 32 (narrow rows measured equal
+// or better with 32: config 1 0.083 against 0.104 ms, config 2 equal).  NLSH_TC_NQ=32/128 overrides (A/B runs).
+int tc_group_size(int64_t n_queries, int32_t p, int32_t n_buckets, int32_t d) {
   const int64_t pairs = n_queries * (int64_t)p;
   const int64_t distinct = pairs < n_buckets ? pairs : n_buckets;
-  int group = (distinct > 0 && pairs >= 64 * distinct) ? kTcNQMax : kTcNQ;
+  int group = (d > 128 && distinct > 0 && pairs >= 64 * distinct) ? kTcNQMax : kTcNQ;
   if (const char* env = getenv("NLSH_TC_NQ")) group = atoi(env) == kTcNQMax ? kTcNQMax : kTcNQ;
   return group;
 }
@@ -1334,7 +1334,7 @@ extern "C" size_t nlsh_query_workspace_bytes(int64_t n_queries, int32_t p, int32
   const ScanPolicy pol = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows);
   int tc_chunks = 0;  // the metric is not an argument: sized for either scan implementation
   if (scan_use_tc(d, k, NLSH_METRIC_L2))
-    tc_chunks = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows, tc_group_size(n_queries, p, n_buckets), 1,
+    tc_chunks = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows, tc_group_size(n_queries, p, n_buckets, d), 1,
                             4ll * ((d + 3) / 4 * 4)).max_chunks;
   return carve_query_ws(nullptr, n_queries, p, k, d, n_buckets, pol.max_chunks, tc_chunks, n_rows).total;
 }
@@ -1366,7 +1366,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
   const ScanPolicy pol_simt = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows);
   const bool tc_sized = scan_use_tc(d, k, NLSH_METRIC_L2);
   ScanPolicy pol_tc = pol_simt;
-  const int tc_group = tc_group_size(n_queries, p, n_buckets);
+  const int tc_group = tc_group_size(n_queries, p, n_buckets, d);
   if (tc_sized) pol_tc = scan_policy(n_queries, p, n_buckets, n_rows, max_bucket_rows, tc_group, 1, 4ll * ((d + 3) / 4 * 4));
   {
     const int64_t pairs64 = n_queries * (int64_t)p;

@@ -185,14 +185,35 @@ struct Ahead {
   float qn2[CH];  // |q|^2 of that query
 };
 
+// What the scorer needs of the kernel arguments, by value (the scorer is one out-of-line function per
+// kernel: three call sites, and its unrolled distance loop is the largest piece of code in the kernel).
+struct ScoreCtx {
+  const float* xs;
+  const int* ids;
+  const float* qs;
+  const int* pq;
+  float* tau_g;
+  const float* tau0;
+  int* ladder;
+  int* cand_n;
+  TcCand* cand;
+  const unsigned char* qbuf;  // shared memory: the item ring's query boxes (not QGLOBAL)
+  const int* qi_s;            // shared memory: the item ring's query indices
+  int cap, k, d, d_pad, kblocks;
+};
+
 // Scores the first n (<= 32) entries of a warp's survivor queue, one per lane, and appends the
 // candidates within their query's bound to its buffer.  Returns nothing; the caller advances the queue.
 // Queue entry: the row of x_sorted and, QGLOBAL, the pair index (query vector = qs[pair], query index =
 // pq[pair]) or else (item slot << 8) | query j of the item whose queries are in shared memory.
+// Inlined at its three call sites: out of line (one copy, less instruction-cache pressure) it measured 10 %
+// faster on config 2 but 10 - 60 % slower on configs 3, 5 and on 8-GPU shards (profiles/r2_experiments).
+#ifndef NLSH_SCORE_INLINE  // A/B: -DNLSH_SCORE_INLINE=__noinline__
+#define NLSH_SCORE_INLINE __forceinline__
+#endif
 template <int METRIC, bool QGLOBAL>
-__device__ __forceinline__ void score_batch(const TcScanArgs& a, const SmemLayout& s, int kblocks,
-                                            const int* q_row, const int* q_meta, unsigned head, int n,
-                                            int lane, unsigned& n_appended) {
+__device__ NLSH_SCORE_INLINE void score_batch(const ScoreCtx a, const int* q_row, const int* q_meta, unsigned head,
+                                         int n, int lane, unsigned& n_appended) {
   if (lane < n) {
     const unsigned e = (head + (unsigned)lane) & (kQueueCap - 1);
     const int row = q_row[e];
@@ -207,9 +228,9 @@ __device__ __forceinline__ void score_batch(const TcScanArgs& a, const SmemLayou
       dist = tc_thread_distance<METRIC, 16>(a.xs + (size_t)row * a.d_pad, q, a.d);
     } else {
       const int islot = meta >> 8, j = meta & 255;
-      qi = s.qi_s[islot * kTcNQ + j];
+      qi = a.qi_s[islot * kTcNQ + j];
       TcQueryShared q;
-      q.base = s.qbuf + (size_t)islot * kblocks * kQBoxBytes + j * 128;
+      q.base = a.qbuf + (size_t)islot * a.kblocks * kQBoxBytes + j * 128;
       q.sw = j & 7;
       dist = tc_thread_distance<METRIC, 16>(a.xs + (size_t)row * a.d_pad, q, a.d);
     }
@@ -391,8 +412,33 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int kb = 0; kb < kblocks; ++kb)
             tma_load_2d(qdst + kb * kQBytes, &map_q, kb * kTcBK, rec.pair_base, &s.q_full[islot]);
         }
-        const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
-        for (int t = 0; t < n_tiles; ++t, ++tcount) {
+      }
+      const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
+      float tau_new[kCh];
+#pragma unroll
+      for (int c = 0; c < kCh; ++c) tau_new[c] = tau_cur[c];
+#pragma unroll 1
+      for (int t = 0; t < n_tiles; ++t, ++tcount) {
+        // Threshold refresh: other items of the same queries (on any SM) lower tau_g while this item is
+        // streamed; once per tile the lanes rewrite the item's thresholds from the value they loaded one
+        // tile earlier (the filter may read the old or the new one: both are upper bounds).
+#ifndef NLSH_NO_REFRESH  // A/B: -DNLSH_NO_REFRESH
+        if (t > 0) {
+#else
+        if (false) {
+#endif
+#pragma unroll
+          for (int c = 0; c < kCh; ++c) {
+            if (32 * c + lane < rec.nq && tau_new[c] < tau_cur[c]) {
+              tau_cur[c] = tau_new[c];
+              s.thr_s[islot * NQ + 32 * c + lane] = make_thr<METRIC>(tau_new[c], cur.qn2[c], a.l2_slack);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < kCh; ++c)
+          if (cur.qi[c] >= 0) tau_new[c] = __ldcg(a.tau_g + cur.qi[c]);
+        if (lane == 0) {
           const int trow0 = rec.row0 + t * kTile;
           {
             // The tile's row norms: a plain bulk copy needs a 16-byte aligned source, so it starts
@@ -431,6 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (WIDE) tma_load_2d(dst + kSlotBytes, &map_q, kb * kTcBK, rec.pair_base, &s.full_bar[sl]);
           }
         }
+        __syncwarp();
       }
       __syncwarp();
       ++icount;
@@ -485,6 +532,23 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int* q_row = s.wq_row + fw * kQueueCap;
     int* q_meta = s.wq_meta + fw * kQueueCap;
+    ScoreCtx sc;
+    sc.xs = a.xs;
+    sc.ids = a.ids;
+    sc.qs = a.qs;
+    sc.pq = a.pq;
+    sc.tau_g = a.tau_g;
+    sc.tau0 = a.tau0;
+    sc.ladder = a.ladder;
+    sc.cand_n = a.cand_n;
+    sc.cand = a.cand;
+    sc.qbuf = s.qbuf;
+    sc.qi_s = s.qi_s;
+    sc.cap = a.cap;
+    sc.k = a.k;
+    sc.d = a.d;
+    sc.d_pad = a.d_pad;
+    sc.kblocks = kblocks;
     unsigned head = 0;  // queue front (index mod kQueueCap)
     int count = 0;      // queued survivors (warp-uniform)
     unsigned n_surv = 0, n_batches = 0, n_flush = 0, n_appended = 0;
@@ -567,7 +631,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             n_surv += (unsigned)added;
             __syncwarp();
             if (count >= 32) {
-              score_batch<METRIC, QGLOBAL>(a, s, kblocks, q_row, q_meta, head, 32, lane, n_appended);
+              score_batch<METRIC, QGLOBAL>(sc, q_row, q_meta, head, 32, lane, n_appended);
               head = (head + 32u) & (kQueueCap - 1);
               count -= 32;
               ++n_batches;
@@ -578,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       // the item's queries leave shared memory with this arrive: score what is still queued
       // (QGLOBAL entries do not refer to the item slot and stay queued across items)
       if (!QGLOBAL && count > 0) {
-        score_batch<METRIC, QGLOBAL>(a, s, kblocks, q_row, q_meta, head, count, lane, n_appended);
+        score_batch<METRIC, QGLOBAL>(sc, q_row, q_meta, head, count, lane, n_appended);
         head = (head + (unsigned)count) & (kQueueCap - 1);
         count = 0;
         ++n_flush;
@@ -588,7 +652,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       ++icount;
     }
     if (QGLOBAL && count > 0) {
-      score_batch<METRIC, QGLOBAL>(a, s, kblocks, q_row, q_meta, head, count, lane, n_appended);
+      score_batch<METRIC, QGLOBAL>(sc, q_row, q_meta, head, count, lane, n_appended);
       ++n_flush;
     }
     if (a.stats != nullptr) {
@@ -906,10 +970,10 @@ int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {
   if (a.nq_group != kTcNQMax) a.nq_group = kTcNQ;
   // wide rows, or 128 queries per item: the queries' K blocks travel with the row tiles
   const bool wide = a.kblocks > kMaxKBlocks || a.nq_group == kTcNQMax;
-  // Scorer query source: the item's shared-memory copy, or (QGLOBAL) the pair-ordered global copy, which
-  // spares the partial batch every warp scores at the end of every item - worth it when items are short
-  // (a few tiles per bucket).  NLSH_TC_QGLOBAL=0/1 overrides (A/B runs).
-  bool qglobal = wide || a.avg_item_rows < 4 * kTile;
+  // Scorer query source: the pair-ordered global copy (QGLOBAL), which spares the partial batch every warp
+  // would score at the end of every item (measured: config 4 0.943 against 0.957 ms, 8-GPU shard 0.191 against
+  // 0.205 ms); NLSH_TC_QGLOBAL=0 selects the item's shared-memory copy instead (A/B runs).
+  bool qglobal = true;
   if (const char* env = getenv("NLSH_TC_QGLOBAL")) qglobal = wide || atoi(env) != 0;
   int n_slots = kMaxSlots;
   // each K block's slot is freed by its own tcgen05.commit, so any ring depth >= 2 makes progress

@@ -12,7 +12,8 @@ import numpy as np
 import torch
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libnlsh_b200.so")
+# NLSH_B200_LIB=<path> loads another build of the library (A/B runs of compile-time variants)
+LIB_PATH = os.environ.get("NLSH_B200_LIB") or os.path.join(_PKG_ROOT, "lib", "libnlsh_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3
 ACT_IDENTITY, ACT_RELU, ACT_SIN = 0, 1, 2
