@@ -64,7 +64,8 @@ def parse_args():
     ap.add_argument("--probes", type=int, default=0, help="fix p instead of searching the ladder")
     ap.add_argument("--fit-steps", type=int, default=300)
     ap.add_argument("--batches-per-step", type=int, default=10, help="query batches per timed step")
-    ap.add_argument("--lanes", type=int, default=2, help="batches in flight in the serving loop")
+    ap.add_argument("--lanes", type=int, default=0,
+                    help="batches in flight in the serving loop (0 = 2 on one GPU, 3 on shards: measured best)")
     ap.add_argument("--cpu-sample", type=int, default=4096,
                     help="queries per step of the reference arm (indexer.py:45-53 multi-probes only full 4096-row batches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -296,7 +297,7 @@ def run_b200(args):
     ids_serial, dists_serial, _ = index.query_tensors(Q, k=k, hash_times=p_used)
 
     # ---- the timed step: nb batches through the serving loop, queries resident in HBM ------------
-    lanes = max(1, args.lanes)
+    lanes = args.lanes if args.lanes > 0 else (2 if world == 1 else 3)
     if args.no_graph:
         pipe = None
 
@@ -372,8 +373,11 @@ def run_b200(args):
         serial_run(Q)
     serial_ms = time_on_stream(lambda: serial_run(Q), 30, device)
     local_ms = serial_ms
-    if world > 1 and hasattr(serial_run, "graphed"):
-        local_ms = time_on_stream(serial_run.graphed.replay, 30, device)
+    if world > 1:  # the same batch without the exchange: this rank's shard alone (hashes all queries itself)
+        local_only = index.local.capture_query(nq, k=k, hash_times=p_used)
+        for _ in range(3):
+            local_only(Q)
+        local_ms = time_on_stream(lambda: local_only(Q), 30, device)
         barrier()
 
     # ---- scan-kernel roofline: CUDA events around the kernel inside the library --------------
@@ -459,10 +463,12 @@ def run_b200(args):
         "clocks": clocks,
         "breakdown_ms_per_batch": {
             "pipelined_batch": batch_ms, "serial_batch": serial_ms, "scan_kernel": scan_avg_ms,
-            "fixed_kernels": local_ms - scan_avg_ms, "exchange_and_merge": serial_ms - local_ms,
-            "note": "serial_batch = one captured batch alone on the device (this rank): scan_kernel + fixed_kernels "
-                    "(query hashing, probe selection, planning, seeding, merge) + exchange_and_merge (NCCL all-gather "
-                    "+ shard merge, N > 1); pipelined_batch = ms_per_step / batches_per_step with the lanes overlapping"},
+            "rest_of_serial_batch": serial_ms - scan_avg_ms, "local_only_batch": local_ms,
+            "note": "serial_batch = one captured batch alone on the device (this rank): scan_kernel + the rest (query "
+                    "hashing - of this rank's 1/N slice of the queries when N > 1 -, probe selection, planning, seeding, "
+                    "candidate merge, and for N > 1 the two captured NCCL all-gathers + the shard merge); local_only_batch "
+                    "= the same batch on this rank's shard without any exchange (it hashes all queries itself); "
+                    "pipelined_batch = ms_per_step / batches_per_step with the lanes overlapping"},
         "roofline": {"bound": "hbm", "kernel": names[scan_impl], "achieved": achieved,
                      "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
@@ -485,13 +491,23 @@ def run_b200(args):
                                         "note": "same call with so few queries that buckets are (almost) never shared"}},
     }
 
-    del pipe, pipe_h
+    for obj in (pipe, pipe_h):
+        if obj is not None:
+            obj.release()
+    g = getattr(serial_run, "graphed", None)
+    if hasattr(g, "release"):
+        g.release()
+    del pipe, pipe_h, serial_run
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_subprocess(args, p_used)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        barrier()
+        sys.stdout.flush()
+        # captured NCCL work can keep destroy_process_group() waiting: the line is printed, leave without it
+        os._exit(0)
 
 
 def cpu_baseline_subprocess(args, p_used):

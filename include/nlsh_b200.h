@@ -142,7 +142,7 @@ int nlsh_build_csr(const int32_t* codes, int64_t n, int32_t n_buckets, const flo
  *   probes    device int32 [n_queries, p]; -1 = unused slot; duplicates inside a row are
  *             scanned once (the reference probes a Python set)
  *   offsets / ids / x_sorted: the CSR produced by nlsh_build_csr (x_sorted row stride d_pad)
- *   x_sqnorm  device fp32 [n_rows] from nlsh_build_csr, or NULL.  With it (and d <= 128, k <= 32)
+ *   x_sqnorm  device fp32 [n_rows] from nlsh_build_csr, or NULL.  With it (and d <= 4096)
  *             the scan runs a tcgen05 tf32 GEMM of each row tile against the bucket's queries as
  *             a FILTER: pairs whose distance lower bound exceeds an upper bound of the query's final
  *             k-th best distance are dropped, the rest are scored exactly as below and the k best
@@ -170,8 +170,32 @@ int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t d, const in
                          float* dists_out, int32_t* ncand_out, void* workspace,
                          size_t workspace_bytes, uint32_t flags, void* stream);
 
+/* The same with the queries' distance bounds supplied: tau_seed device fp32 [n_queries] (or NULL = compute them
+ * here), each an upper bound of the query's final k-th best distance in the scan's units (squared for L2), e.g.
+ * from nlsh_query_seed_tau on ANY shard of the database: k rows within the bound exist somewhere, so no shard
+ * needs candidates beyond it.  Row-sharded search (nlsh/parallel.py) lets each rank seed 1/N of the queries and
+ * all-gathers the bounds with the probe matrix.  Only the tensor-core scan uses them; results do not change. */
+int nlsh_query_scan_topk_seeded(const float* xq, int64_t n_queries, int32_t d, const int32_t* probes,
+                                int32_t p, const int32_t* offsets, int32_t n_buckets, const int32_t* ids,
+                                const float* x_sorted, const float* x_sqnorm, int64_t n_rows,
+                                int64_t max_bucket_rows, int32_t metric, int32_t k, int64_t id_offset,
+                                const float* tau_seed, int64_t* ids_out, float* dists_out,
+                                int32_t* ncand_out, void* workspace, size_t workspace_bytes, uint32_t flags,
+                                void* stream);
+
+/* Distance bounds of a batch of queries from a sample of the rows of their probed buckets (the seed of the
+ * tensor-core scan's filter, scan_tc.cu::seed_tau_kernel): tau_out[q] = the exact k-th best distance of query q
+ * among the first rows of its probed buckets (in the scan's units, inflated by the rounding bound of another
+ * summation order), +inf when they hold fewer than k rows.  No reference counterpart (the reference scores
+ * every candidate, nlsh/indexer.py:84-91). */
+size_t nlsh_query_seed_workspace_bytes(int64_t n_queries, int32_t d);
+int nlsh_query_seed_tau(const float* xq, int64_t n_queries, int32_t d, const int32_t* probes, int32_t p,
+                        const int32_t* offsets, int32_t n_buckets, const float* x_sorted, int64_t n_rows,
+                        int32_t metric, int32_t k, float* tau_out, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* Which kernel nlsh_query_scan_topk runs for this shape with / without x_sqnorm and default flags:
- * 1 = tensor-core filtered scan (scan_tc.cu: d <= 128, k <= 32 and at least ~4 (query, probe) pairs
+ * 1 = tensor-core filtered scan (scan_tc.cu: d <= 4096, k <= 128 and at least ~4 (query, probe) pairs
  * per bucket, i.e. bucket tiles are shared between queries), 0 = fp32 SIMT scan (scan.cu). */
 int nlsh_query_scan_impl(int32_t d, int32_t k, int32_t metric, int32_t has_sqnorm, int64_t n_queries,
                          int32_t p, int32_t n_buckets);

@@ -1339,6 +1339,43 @@ extern "C" size_t nlsh_query_workspace_bytes(int64_t n_queries, int32_t p, int32
   return carve_query_ws(nullptr, n_queries, p, k, d, n_buckets, pol.max_chunks, tc_chunks, n_rows).total;
 }
 
+extern "C" size_t nlsh_query_seed_workspace_bytes(int64_t n_queries, int32_t d) {
+  if (n_queries < 0 || d < 1) return 0;
+  WorkspaceCarver ws(nullptr);
+  ws.take<float>((size_t)n_queries * ((d + 3) / 4 * 4));
+  ws.take<float>((size_t)n_queries);
+  return ws.total();
+}
+
+extern "C" int nlsh_query_seed_tau(const float* xq, int64_t n_queries, int32_t d, const int32_t* probes,
+                                   int32_t p, const int32_t* offsets, int32_t n_buckets,
+                                   const float* x_sorted, int64_t n_rows, int32_t metric, int32_t k,
+                                   float* tau_out, void* workspace, size_t workspace_bytes, void* stream) {
+  NLSH_REQUIRE(n_queries >= 0 && d >= 1 && d <= 16384 && p >= 1 && p <= 1024, "seed: bad shape");
+  NLSH_REQUIRE(k >= 1 && k <= NLSH_MAX_K, "seed: k=%d outside [1, %d]", k, NLSH_MAX_K);
+  NLSH_REQUIRE(n_buckets >= 1 && n_buckets <= (1 << 20), "seed: n_buckets=%d outside [1, 2^20]", n_buckets);
+  NLSH_REQUIRE(metric == NLSH_METRIC_L2 || metric == NLSH_METRIC_ANGULAR, "seed: metric %d is not a scan metric",
+               metric);
+  if (n_queries == 0) return NLSH_OK;
+  NLSH_REQUIRE(xq && probes && offsets && tau_out && (n_rows == 0 || x_sorted), "seed: null pointer");
+  NLSH_REQUIRE(nlsh_scan_tc_supported(d, k, metric), "seed: shape outside the tensor-core scan (d=%d, k=%d)", d, k);
+  const size_t need = nlsh_query_seed_workspace_bytes(n_queries, d);
+  if (workspace == nullptr || workspace_bytes < need) {
+    nlsh_set_error("seed: workspace %zu bytes < required %zu", workspace_bytes, need);
+    return NLSH_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d_pad = (d + 3) / 4 * 4;
+  WorkspaceCarver ws(workspace);
+  float* qn = ws.take<float>((size_t)n_queries * d_pad);
+  float* tau_g = ws.take<float>((size_t)n_queries);
+  prepare_queries_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(
+      xq, n_queries, d, d_pad, metric == NLSH_METRIC_ANGULAR ? 1 : 0, qn);
+  NLSH_CUDA_TRY(nlsh_post_launch());
+  return nlsh_scan_tc_seed(qn, n_queries, probes, p, offsets, x_sorted, n_rows, n_buckets, d, d_pad, k, metric,
+                           tau_g, tau_out, st);
+}
+
 extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t d,
                                     const int32_t* probes, int32_t p, const int32_t* offsets,
                                     int32_t n_buckets, const int32_t* ids, const float* x_sorted,
@@ -1347,6 +1384,19 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
                                     int32_t k, int64_t id_offset, int64_t* ids_out,
                                     float* dists_out, int32_t* ncand_out, void* workspace,
                                     size_t workspace_bytes, uint32_t flags, void* stream) {
+  return nlsh_query_scan_topk_seeded(xq, n_queries, d, probes, p, offsets, n_buckets, ids, x_sorted, x_sqnorm,
+                                     n_rows, max_bucket_rows, metric, k, id_offset, nullptr, ids_out, dists_out,
+                                     ncand_out, workspace, workspace_bytes, flags, stream);
+}
+
+extern "C" int nlsh_query_scan_topk_seeded(const float* xq, int64_t n_queries, int32_t d,
+                                           const int32_t* probes, int32_t p, const int32_t* offsets,
+                                           int32_t n_buckets, const int32_t* ids, const float* x_sorted,
+                                           const float* x_sqnorm, int64_t n_rows, int64_t max_bucket_rows,
+                                           int32_t metric, int32_t k, int64_t id_offset,
+                                           const float* tau_seed, int64_t* ids_out, float* dists_out,
+                                           int32_t* ncand_out, void* workspace, size_t workspace_bytes,
+                                           uint32_t flags, void* stream) {
   NLSH_REQUIRE(n_queries >= 0 && n_queries * (int64_t)p < (1ll << 31),
                "query: n_queries=%lld x p=%d outside [0, 2^31)", (long long)n_queries, p);
   NLSH_REQUIRE(d >= 1 && d <= 16384, "query: d=%d outside [1, 16384]", d);
@@ -1414,7 +1464,7 @@ extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t 
                                                              w.max_tc_items);
     NLSH_CUDA_TRY(nlsh_post_launch());
     int rc = nlsh_scan_tc_prepare(w.qn, w.pairs, w.pair_off + n_buckets, n_pairs, p, geom.d_pad, w.qs, w.pq,
-                                  w.pqn2, w.tau_g, w.tau0, n_queries, probes, offsets, x_sorted, n_rows,
+                                  w.pqn2, w.tau_g, w.tau0, tau_seed, n_queries, probes, offsets, x_sorted, n_rows,
                                   n_buckets, geom.d, k, metric, st);
     if (rc != NLSH_OK) return rc;
     unsigned long long* stats =

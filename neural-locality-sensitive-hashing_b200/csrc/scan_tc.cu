@@ -895,10 +895,23 @@ bool nlsh_scan_tc_supported(int d, int k, int metric) {
          (metric == NLSH_METRIC_L2 || metric == NLSH_METRIC_ANGULAR);
 }
 
+namespace {
+__global__ void copy_tau_kernel(const float* __restrict__ src, long long n, float* __restrict__ tau_g,
+                                float* __restrict__ tau0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float t = src[i];
+    tau_g[i] = t;
+    tau0[i] = t;
+  }
+}
+}  // namespace
+
 int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, long long n_pairs,
                          int p, int d_pad, float* qs, int* pq, float* pqn2, float* tau_g, float* tau0,
-                         long long n_queries, const int* probes, const int* offsets, const float* xs,
-                         long long n_rows, int n_buckets, int d, int k, int metric, cudaStream_t st) {
+                         const float* tau_seed, long long n_queries, const int* probes, const int* offsets,
+                         const float* xs, long long n_rows, int n_buckets, int d, int k, int metric,
+                         cudaStream_t st) {
   long long blocks = (n_pairs * 32 + 255) / 256;
   const long long cap = (long long)nlsh_num_sms() * 16;
   if (blocks > cap) blocks = cap;
@@ -906,6 +919,17 @@ int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, 
   gather_pair_queries_kernel<<<(unsigned)blocks, 256, 0, st>>>(qn, pairs, n_valid, n_pairs, p, d_pad, qs, pq,
                                                              pqn2);
   NLSH_CUDA_TRY(nlsh_post_launch());
+  if (tau_seed != nullptr) {  // bounds computed elsewhere (another rank's slice of the seeding)
+    copy_tau_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, st>>>(tau_seed, n_queries, tau_g, tau0);
+    return nlsh_check_cuda(nlsh_post_launch(), "copy_tau_kernel launch");
+  }
+  return nlsh_scan_tc_seed(qn, n_queries, probes, p, offsets, xs, n_rows, n_buckets, d, d_pad, k, metric, tau_g,
+                           tau0, st);
+}
+
+int nlsh_scan_tc_seed(const float* qn, long long n_queries, const int* probes, int p, const int* offsets,
+                      const float* xs, long long n_rows, int n_buckets, int d, int d_pad, int k, int metric,
+                      float* tau_g, float* tau0, cudaStream_t st) {
   // Sample rows per query: half the average bucket, 32 .. 128, and at least 1/seed_div of the query's own
   // first bucket (2441-row buckets: 152 rows), so that the rows of a large bucket that fall below the bound
   // stay a few dozen.  The scan's time hardly depends on the survivors (config 4: 1.08 M survivors 0.96 ms,

@@ -53,13 +53,18 @@ struct TcScanArgs {
 };
 
 bool nlsh_scan_tc_supported(int d, int k, int metric);
-// tau_g[q] = tau0[q] = the exact k-th best distance of query q among the first rows of its probed buckets
-// (+inf when they hold < k rows), inflated by the rounding bound of a different summation order;
-// qs[i] = qn[pairs[i] / p], pq[i] = pairs[i] / p, pqn2[i] = |qs[i]|^2 for i < *n_valid.
+// nlsh_scan_tc_seed: tau_g[q] = tau0[q] = the exact k-th best distance of query q among the first rows of
+// its probed buckets (+inf when they hold < k rows), inflated by the rounding bound of a different summation
+// order.  nlsh_scan_tc_prepare: qs[i] = qn[pairs[i] / p], pq[i] = pairs[i] / p, pqn2[i] = |qs[i]|^2 for
+// i < *n_valid, then the seed - or, with tau_seed != NULL, tau_g = tau0 = tau_seed (bounds from elsewhere).
+int nlsh_scan_tc_seed(const float* qn, long long n_queries, const int* probes, int p, const int* offsets,
+                      const float* xs, long long n_rows, int n_buckets, int d, int d_pad, int k, int metric,
+                      float* tau_g, float* tau0, cudaStream_t st);
 int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, long long n_pairs,
                          int p, int d_pad, float* qs, int* pq, float* pqn2, float* tau_g, float* tau0,
-                         long long n_queries, const int* probes, const int* offsets, const float* xs,
-                         long long n_rows, int n_buckets, int d, int k, int metric, cudaStream_t st);
+                         const float* tau_seed, long long n_queries, const int* probes, const int* offsets,
+                         const float* xs, long long n_rows, int n_buckets, int d, int k, int metric,
+                         cudaStream_t st);
 int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st);
 
 #ifdef __CUDACC__

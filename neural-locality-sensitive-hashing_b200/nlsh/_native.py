@@ -61,6 +61,12 @@ PROTOTYPES = {
     "nlsh_query_scan_topk": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64,
                                             _i64, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _u32,
                                             _vp]),
+    "nlsh_query_scan_topk_seeded": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64,
+                                                   _i64, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _u32,
+                                                   _vp]),
+    "nlsh_query_seed_workspace_bytes": (_sz, [_i64, _i32]),
+    "nlsh_query_seed_tau": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _i64, _i32, _i32, _vp, _vp,
+                                           _sz, _vp]),
     "nlsh_query_scan_impl": (ctypes.c_int, [_i32, _i32, _i32, _i32, _i64, _i32, _i32]),
     "nlsh_knn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "nlsh_knn_bruteforce": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _i64,
@@ -322,11 +328,29 @@ def build_csr(codes, n_buckets, x=None, want_sqnorm=False, workspace=None):
 # --------------------------------------------------------------------------------------
 # query / kNN / merge
 # --------------------------------------------------------------------------------------
+def query_seed_tau(xq, probes, offsets, x_sorted, d, metric, k, workspace=None):
+    """Distance bounds fp32 [Q] of the queries from a sample of the rows of their probed buckets (the seed of
+    the tensor-core scan's filter); valid for any shard of the same database (query_scan_topk(tau_seed=...))."""
+    xq = _f32c(xq, "query_vectors")
+    require_cuda(probes, "probes")
+    probes = probes.to(torch.int32).contiguous()
+    nq = xq.shape[0]
+    tau = torch.empty((nq,), dtype=torch.float32, device=xq.device)
+    with torch.cuda.device(xq.device):
+        nbytes = lib().nlsh_query_seed_workspace_bytes(nq, d)
+        ws = _workspace(xq.device, nbytes, workspace)
+        rc = lib().nlsh_query_seed_tau(_ptr(xq), nq, d, _ptr(probes), probes.shape[1], _ptr(offsets),
+                                       offsets.shape[0] - 1, _ptr(x_sorted), x_sorted.shape[0], metric, k,
+                                       _ptr(tau), _ptr(ws), ws.numel(), _stream())
+    _check(rc, "nlsh_query_seed_tau")
+    return tau
+
+
 def query_scan_topk(xq, probes, offsets, ids, x_sorted, d, max_bucket_rows, metric, k,
-                    id_offset=0, flags=0, out=None, x_sqnorm=None, workspace=None):
+                    id_offset=0, flags=0, out=None, x_sqnorm=None, workspace=None, tau_seed=None):
     """-> (ids int64 [Q, k], dists fp32 [Q, k], n_cand int32 [Q]); `out` = preallocated
     contiguous (ids, dists, n_cand) tensors to write into; x_sqnorm (from build_csr) enables the
-    tensor-core filtered scan."""
+    tensor-core filtered scan; tau_seed fp32 [Q] = distance bounds from query_seed_tau (any shard)."""
     xq = _f32c(xq, "query_vectors")
     require_cuda(probes, "probes")
     probes = probes.to(torch.int32).contiguous()
@@ -349,11 +373,14 @@ def query_scan_topk(xq, probes, offsets, ids, x_sorted, d, max_bucket_rows, metr
     with torch.cuda.device(dev):
         nbytes = lib().nlsh_query_workspace_bytes(nq, p, k, d, n_buckets, n_rows, max_bucket_rows)
         ws = _workspace(dev, nbytes, workspace)
-        rc = lib().nlsh_query_scan_topk(_ptr(xq), nq, d, _ptr(probes), p, _ptr(offsets), n_buckets,
-                                        _ptr(ids), _ptr(x_sorted), _ptr(x_sqnorm), n_rows,
-                                        max_bucket_rows, metric,
-                                        k, id_offset, _ptr(out_ids), _ptr(out_d), _ptr(out_n),
-                                        _ptr(ws), ws.numel(), flags, _stream())
+        if tau_seed is not None:
+            require_cuda(tau_seed, "tau_seed")
+            assert tau_seed.dtype == torch.float32 and tau_seed.shape == (nq,) and tau_seed.is_contiguous()
+        rc = lib().nlsh_query_scan_topk_seeded(_ptr(xq), nq, d, _ptr(probes), p, _ptr(offsets), n_buckets,
+                                               _ptr(ids), _ptr(x_sorted), _ptr(x_sqnorm), n_rows,
+                                               max_bucket_rows, metric,
+                                               k, id_offset, _ptr(tau_seed), _ptr(out_ids), _ptr(out_d),
+                                               _ptr(out_n), _ptr(ws), ws.numel(), flags, _stream())
     _check(rc, "nlsh_query_scan_topk")
     return out_ids, out_d, out_n
 

@@ -206,7 +206,19 @@ class Indexer:
         return codes_to_sets(self.hash_tensors(query_vectors, hash_times))
 
     # ---- query ---------------------------------------------------------------------------
-    def query_tensors(self, query_vectors, k=10, hash_times=10, probes=None, out=None, workspace=None):
+    def seed_tau_tensors(self, query_vectors, probes, k=10, workspace=None):
+        """Distance bounds fp32 [Q] of the queries from a sample of this index's rows (see
+        _native.query_seed_tau): upper bounds of the k-th best distance over ANY index that holds these rows,
+        so a row-sharded search seeds each query on one rank only."""
+        return _native.query_seed_tau(query_vectors, probes, self._offsets, self._x_sorted, self._dim,
+                                      self._metric, k, workspace=workspace)
+
+    def uses_tensor_core_scan(self, n_queries, k, hash_times):
+        return _native.scan_impl(self._dim, k, self._metric, self._x_sqnorm is not None, n_queries, hash_times,
+                                 self._hashing.n_buckets) == 1 and (self.scan_flags & 2) == 0
+
+    def query_tensors(self, query_vectors, k=10, hash_times=10, probes=None, out=None, workspace=None,
+                      tau_seed=None):
         """Batched search -> (ids int64 [Q, k], dists fp32 [Q, k], n_candidates int32 [Q]),
         all on the device, no host synchronisation.  ids are -1 / dists +inf past the number
         of candidates.  `probes` (int32 [Q, p], -1 = unused) overrides the hasher's probe
@@ -218,7 +230,7 @@ class Indexer:
         return _native.query_scan_topk(
             query_vectors, probes, self._offsets, self._ids, self._x_sorted, self._dim,
             self._max_bucket_rows, self._metric, k, id_offset=self._id_offset,
-            flags=self.scan_flags, out=out, x_sqnorm=self._x_sqnorm, workspace=workspace)
+            flags=self.scan_flags, out=out, x_sqnorm=self._x_sqnorm, workspace=workspace, tau_seed=tau_seed)
 
     def query(self, query_vectors, k=10, hash_times=10, probes=None) -> List[List[int]]:
         # indexer.py:56-96: returns (List[List[int]] ids by ascending distance, List[int]

@@ -90,26 +90,29 @@ class ShardedIndexer:
         self.local.query_tensors(query_vectors, k, hash_times, probes, out=packed.out())
         return packed.exchange_and_merge(self.group)
 
-    def capture_query(self, n_queries, k=10, hash_times=10):
-        """The local search (hash -> scan + top-k) as one CUDA graph; the all-gather and the
-        merge of the shard lists stay eager launches behind it.  Returns a callable
-        query_vectors -> (ids, dists, n_candidates); `.kernels_per_call` counts this library's
-        kernels per call."""
-        multi = self._multi()
-        packed = None
-        if multi:
-            dev = self.local._candidate_vectors_gpu.device
-            packed = PackedLists(n_queries, k, dist.get_world_size(self.group), dev)
-        graphed = self.local.capture_query(n_queries, k, hash_times,
-                                           out=packed.out() if multi else None)
+    def capture_query(self, n_queries, k=10, hash_times=10, shard_hashing=True, group=None):
+        """The whole batch as ONE CUDA graph.  One rank: hash -> probe selection -> scan + top-k.  Several ranks:
+        each rank hashes its 1/N slice of the queries, the probe matrices meet in a first all-gather (Q x p int32),
+        every rank scans its shard, the packed per-shard lists meet in the second all-gather, then the shard merge -
+        NCCL collectives captured in the graph, so a replay costs one launch and no host work between the kernels.
+        (`shard_hashing=False`: every rank hashes all queries, one all-gather.  `group`: the process group of the
+        captured collectives - graphs that replay concurrently need a communicator each.)  Returns a callable
+        query_vectors -> (ids, dists, n_candidates); `.kernels_per_call` counts this library's kernels per call."""
+        if not self._multi():
+            graphed = self.local.capture_query(n_queries, k, hash_times)
+
+            def run(query_vectors):
+                return graphed(query_vectors)
+
+            run.kernels_per_call = graphed.kernels_per_replay
+            run.graphed = graphed
+            return run
+        graphed = GraphedShardedQuery(self, n_queries, k, hash_times, shard_hashing, group=group)
 
         def run(query_vectors):
-            res = graphed(query_vectors)
-            if not multi:
-                return res
-            return packed.exchange_and_merge(self.group)  # ONE all-gather + the merge kernel
+            return graphed(query_vectors)
 
-        run.kernels_per_call = graphed.kernels_per_replay + (1 if multi else 0)
+        run.kernels_per_call = graphed.kernels_per_replay
         run.graphed = graphed
         return run
 
@@ -117,6 +120,77 @@ class ShardedIndexer:
         ids, _, ncand = self.query_tensors(query_vectors, k, hash_times, probes)
         rows = ids.cpu().tolist()
         return [[v for v in r if v >= 0] for r in rows], ncand.cpu().tolist()
+
+
+class GraphedShardedQuery:
+    """One batch of a row-sharded search as a single CUDA graph (see ShardedIndexer.capture_query).  The
+    graph owns its scratch workspace, its padded query buffer, the probe and result exchange buffers and the
+    output tensors; the NCCL all-gathers are graph nodes (captured with capture_error_mode="thread_local":
+    the process group's watchdog thread may touch CUDA while this thread captures)."""
+
+    def __init__(self, sharded, n_queries, k, hash_times, shard_hashing=True, group=None):
+        local = sharded.local
+        dev = local._candidate_vectors_gpu.device
+        group = group if group is not None else sharded.group
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        self.n_queries = n_queries
+        self.chunk = (n_queries + world - 1) // world if shard_hashing else n_queries
+        rows = self.chunk * world if shard_hashing else n_queries
+        self.q = torch.zeros((rows, local._dim), dtype=torch.float32, device=dev)
+        self.workspace = _native.Workspace(dev, name=f"GraphedShardedQuery {id(self):#x}")
+        self.packed = PackedLists(n_queries, k, world, dev)
+        # first exchange: per query its probe row and, in one more int32 column, the bits of its distance bound
+        # (each rank seeds the bounds of its slice from its own shard: valid for every shard)
+        seeded = shard_hashing and local.uses_tensor_core_scan(n_queries, k, hash_times)
+        width = hash_times + (1 if seeded else 0)
+        self.slice_out = torch.empty((self.chunk, width), dtype=torch.int32, device=dev)
+        self.slices_all = torch.empty((rows, width), dtype=torch.int32, device=dev)
+
+        def batch():
+            if shard_hashing:
+                mine = self.q[rank * self.chunk:(rank + 1) * self.chunk]
+                probes_mine = local.hash_tensors(mine, hash_times, workspace=self.workspace)
+                self.slice_out[:, :hash_times] = probes_mine
+                if seeded:
+                    tau_mine = local.seed_tau_tensors(mine, probes_mine, k, workspace=self.workspace)
+                    self.slice_out[:, hash_times] = tau_mine.view(torch.int32)
+                dist.all_gather_into_tensor(self.slices_all, self.slice_out, group=group)
+                probes = self.slices_all[:n_queries, :hash_times].contiguous()
+                tau = self.slices_all[:n_queries, hash_times].contiguous().view(torch.float32) if seeded else None
+            else:
+                probes = local.hash_tensors(self.q, hash_times, workspace=self.workspace)
+                tau = None
+            local.query_tensors(self.q[:n_queries], k, hash_times, probes=probes, out=self.packed.out(),
+                                workspace=self.workspace, tau_seed=tau)
+            return self.packed.exchange_and_merge(group)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up on the capture stream: sizes the workspace, warms the communicator
+            for _ in range(2):
+                batch()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        launches0 = _native.kernel_launch_count()
+        with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
+            self.ids, self.dists, self.ncand = batch()
+        self.kernels_per_replay = _native.kernel_launch_count() - launches0
+        self.workspace.frozen = True
+
+    def replay(self):
+        self.graph.replay()
+        return self.ids, self.dists, self.ncand
+
+    def __call__(self, query_vectors):
+        self.q[:self.n_queries].copy_(query_vectors, non_blocking=True)
+        self.graph.replay()
+        return self.ids, self.dists, self.ncand
+
+    def release(self):
+        """Drop the captured graph (before the process group is destroyed: a live graph holds NCCL work)."""
+        self.graph = None
 
 
 class PipelinedSearch:
@@ -143,10 +217,15 @@ class PipelinedSearch:
         self.to_host = bool(to_host)
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.depth)]
         self.runs = []
-        for st in self.streams:
+        multi = sharded_index._multi()
+        # lanes replay concurrently: NCCL serialises nothing between the captured collectives of different
+        # graphs, so every lane gets a communicator of its own (all ranks create them in the same order)
+        self.groups = [dist.new_group() if multi and self.depth > 1 else sharded_index.group
+                       for _ in range(self.depth)]
+        for st, grp in zip(self.streams, self.groups):
             st.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(st):
-                self.runs.append(sharded_index.capture_query(n_queries, k=k, hash_times=hash_times))
+                self.runs.append(sharded_index.capture_query(n_queries, k=k, hash_times=hash_times, group=grp))
         torch.cuda.synchronize(dev)
         self.out = [(torch.empty((n_queries, k), dtype=torch.int64).pin_memory(),
                      torch.empty((n_queries, k), dtype=torch.float32).pin_memory(),
@@ -178,6 +257,15 @@ class PipelinedSearch:
     def result(self, ticket):
         self.done[ticket].synchronize()
         return self.out[ticket] if self.to_host else self.dev_out[ticket]
+
+    def release(self):
+        """Drop the lanes' captured graphs (before the process group is destroyed)."""
+        torch.cuda.synchronize(self.device)
+        for run in self.runs:
+            g = getattr(run, "graphed", None)
+            if hasattr(g, "release"):
+                g.release()
+        self.runs = []
 
     def fence(self):
         """Orders the current stream after everything submitted so far (no host wait)."""

@@ -71,7 +71,7 @@ def test_hash_codes_error_behaviour():
 
 
 def test_scan_kernel_choice_is_a_pure_host_decision(monkeypatch):
-    """nlsh_query_scan_impl: tensor-core filter for d <= 128, k <= 32, L2 / angular, row norms present and
+    """nlsh_query_scan_impl: tensor-core filter for L2 / angular with k <= 128, d <= 4096, row norms present and
     bucket tiles shared by >= 4 (query, probe) pairs on average; fp32 SIMT scan otherwise."""
     from nlsh import _native
     monkeypatch.delenv("NLSH_SCAN_IMPL", raising=False)
@@ -80,9 +80,10 @@ def test_scan_kernel_choice_is_a_pure_host_decision(monkeypatch):
     assert _native.scan_impl(100, 10, ANG, True, 10_000, 2, 1024) == 1     # config 3
     assert _native.scan_impl(128, 10, L2, True, 256, 8, 4096) == 0         # about one query per bucket
     assert _native.scan_impl(128, 10, L2, False, 10_000, 8, 4096) == 0     # index without row norms
-    assert _native.scan_impl(960, 100, L2, True, 1000, 128, 512) == 0      # config 5: wide rows, k = 100
-    assert _native.scan_impl(128, 33, L2, True, 10_000, 8, 4096) == 0
-    assert _native.scan_impl(132, 10, L2, True, 10_000, 8, 4096) == 0
+    assert _native.scan_impl(960, 100, L2, True, 1000, 128, 512) == 1      # config 5: wide rows, k = 100
+    assert _native.scan_impl(128, 33, L2, True, 10_000, 8, 4096) == 1
+    assert _native.scan_impl(132, 10, L2, True, 10_000, 8, 4096) == 1
+    assert _native.scan_impl(4100, 10, L2, True, 10_000, 8, 4096) == 0     # wider than 128 K blocks
     monkeypatch.setenv("NLSH_SCAN_IMPL", "simt")
     assert _native.scan_impl(128, 10, L2, True, 10_000, 8, 4096) == 0
     monkeypatch.setenv("NLSH_SCAN_IMPL", "tc")
