@@ -65,7 +65,7 @@ def parse_args():
     ap.add_argument("--fit-steps", type=int, default=300)
     ap.add_argument("--batches-per-step", type=int, default=10, help="query batches per timed step")
     ap.add_argument("--lanes", type=int, default=0,
-                    help="batches in flight in the serving loop (0 = 2 on one GPU, 3 on shards: measured best)")
+                    help="batches in flight in the serving loop (0 = 2 on one GPU, 3 on 2, 4 on 4 or 8: measured best)")
     ap.add_argument("--cpu-sample", type=int, default=4096,
                     help="queries per step of the reference arm (indexer.py:45-53 multi-probes only full 4096-row batches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -105,7 +105,8 @@ def make_hashing(d, hs, metric, seed, device, fit_steps, src_rank_trains=True, s
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the bench is under load."""
+    """nvidia-smi clocks / throttle reasons of one GPU sampled every 200 ms while the bench is under load (rank 0
+    only: one poller per rank stalls the ranks in turn, and the captured collectives make every rank wait)."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -121,7 +122,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100", "-f", self.path],
+                 "--format=csv,noheader,nounits", "-lms", "200", "-f", self.path],
                 stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -297,7 +298,7 @@ def run_b200(args):
     ids_serial, dists_serial, _ = index.query_tensors(Q, k=k, hash_times=p_used)
 
     # ---- the timed step: nb batches through the serving loop, queries resident in HBM ------------
-    lanes = args.lanes if args.lanes > 0 else (2 if world == 1 else 3)
+    lanes = args.lanes if args.lanes > 0 else (2 if world == 1 else (3 if world < 4 else 4))
     if args.no_graph:
         pipe = None
 
@@ -319,7 +320,8 @@ def run_b200(args):
         assert torch.equal(p_ids, ids_serial) and torch.equal(p_d, dists_serial), "pipelined != serial results"
 
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     launches0 = _native.kernel_launch_count()
@@ -401,10 +403,9 @@ def run_b200(args):
     # nvidia-smi needs about a second to deliver its first sample; the timed region is shorter than
     # that: keep the same step running, untimed, until a few samples exist (a fixed number of steps
     # derived from the rank-maximum step time, so that every rank issues the same number of all-gathers)
-    if sampler.proc is not None:
-        for _ in range(int(min(2000, max(0.0, 1500.0 / max(ms / args.steps, 1e-3))))):
-            step()
-        torch.cuda.synchronize()
+    for _ in range(int(min(2000, max(0.0, 1500.0 / max(ms / args.steps, 1e-3))))):
+        step()
+    torch.cuda.synchronize()
     clocks = sampler.stop()
 
     sizes_dev = torch.from_numpy(sizes_host).to(device)

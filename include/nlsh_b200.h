@@ -156,6 +156,9 @@ int nlsh_build_csr(const int32_t* codes, int64_t n, int32_t n_buckets, const flo
  *          bit 1 = do not use the tensor-core filter even when x_sqnorm is given (debug / A-B only);
  *          bit 2 = tensor-core scan with candidate buffers of only k entries per query, so that
  *                  (almost) every query takes the exact re-scan of the overflow path (tests only);
+ *          bit 3 = L2: leave the SQUARED distances in dists_out (a caller that merges the lists of several
+ *                  shards takes the root after the merge: two candidates whose roots round to the same
+ *                  float then keep the order of their squared distances, as in an unsharded search);
  *          bits 8-15 = number of SMs the tensor-core scan's persistent grid leaves free for kernels of
  *                  other streams (batches in flight on several streams overlap the launch-bound front
  *                  part of one batch with the scan of another; 0 = use every SM)

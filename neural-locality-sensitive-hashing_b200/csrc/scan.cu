@@ -891,7 +891,7 @@ __global__ void __launch_bounds__(32 * kMergeWarps)
                        const float* __restrict__ qn, const float* __restrict__ xs,
                        const int* __restrict__ row_ids, const int* __restrict__ probes,
                        const int* __restrict__ offsets, int n_buckets, int p, int k, int d, int d_pad,
-                       int metric, long long n_queries, long long id_offset, const float* __restrict__ tau_g,
+                       int metric, int sqrt_out, long long n_queries, long long id_offset, const float* __restrict__ tau_g,
                        long long* __restrict__ ids_out, float* __restrict__ dists_out,
                        int* __restrict__ ncand_out, unsigned long long* __restrict__ stats) {
   __shared__ int ovf_q[kMergeWarps];
@@ -934,7 +934,7 @@ __global__ void __launch_bounds__(32 * kMergeWarps)
         if (pos < k) {
           const int id = top.id[j];
           ids_out[q * k + pos] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
-          dists_out[q * k + pos] = metric == NLSH_METRIC_L2 ? sqrtf(top.d[j]) : top.d[j];
+          dists_out[q * k + pos] = sqrt_out ? sqrtf(top.d[j]) : top.d[j];
         }
       }
     } else if (lane == 0) {
@@ -985,7 +985,7 @@ __global__ void __launch_bounds__(32 * kMergeWarps)
         if (pos < k) {
           const int id = top.id[j];
           ids_out[oq * k + pos] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
-          dists_out[oq * k + pos] = metric == NLSH_METRIC_L2 ? sqrtf(top.d[j]) : top.d[j];
+          dists_out[oq * k + pos] = sqrt_out ? sqrtf(top.d[j]) : top.d[j];
         }
       }
     }
@@ -1434,6 +1434,10 @@ extern "C" int nlsh_query_scan_topk_seeded(const float* xq, int64_t n_queries, i
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool async = (flags & 1u) == 0;
+  // L2 lists hold squared distances; the root is taken when a query's list is written - unless the caller
+  // merges lists of several shards and takes it afterwards (flags bit 3), so that two candidates whose roots
+  // round to the same float keep the order of their squared distances across the shard merge
+  const int sqrt_scores = (metric == NLSH_METRIC_L2 && (flags & 8u) == 0) ? 1 : 0;
   // tensor-core filtered scan (scan_tc.cu) whenever the index carries the row norms
   const bool use_tc = tc_sized && async && (flags & 2u) == 0 && x_sqnorm != nullptr && n_rows > 0 &&
                       (reinterpret_cast<uintptr_t>(x_sqnorm) & 15) == 0 && scan_use_tc(d, k, metric) &&
@@ -1504,7 +1508,7 @@ extern "C" int nlsh_query_scan_topk_seeded(const float* xq, int64_t n_queries, i
     if (rc != NLSH_OK) return rc;
     const unsigned mblocks = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
 #define NLSH_MERGE_ARGS w.cand, w.cand_n, cap, w.qn, x_sorted, ids, probes, offsets, n_buckets, p, k, geom.d, geom.d_pad, \
-                        metric, n_queries, id_offset, w.tau_g, reinterpret_cast<long long*>(ids_out), dists_out, ncand_out, stats
+                        metric, sqrt_scores, n_queries, id_offset, w.tau_g, reinterpret_cast<long long*>(ids_out), dists_out, ncand_out, stats
     if (k <= 32) merge_cands_kernel<1><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
     else if (k <= 64) merge_cands_kernel<2><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
     else merge_cands_kernel<4><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
@@ -1549,7 +1553,7 @@ extern "C" int nlsh_query_scan_topk_seeded(const float* xq, int64_t n_queries, i
   nlsh_profile_mark(st, false);
   if (rc != NLSH_OK) return rc;
   return launch_merge_partials(w.part_d, w.part_id, probes, offsets, n_buckets, p, k, pol.rchunk,
-                               pol.max_chunks, 0, metric == NLSH_METRIC_L2 ? 1 : 0, n_queries,
+                               pol.max_chunks, 0, sqrt_scores, n_queries,
                                id_offset, ids_out, dists_out, ncand_out, st);
 }
 

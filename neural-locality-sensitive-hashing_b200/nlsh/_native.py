@@ -22,6 +22,9 @@ METRIC_L2, METRIC_ANGULAR, METRIC_L2SQ, METRIC_COSINE = 0, 1, 2, 3
 MAX_K = 128
 MAX_HASH_BITS = 15
 FLAG_SYNC_STAGING = 1
+FLAG_NO_TC_FILTER = 2
+FLAG_TINY_CAND_BUFFERS = 4
+FLAG_SQUARED_L2_OUT = 8
 
 METRIC_BY_NAME = {"l2": METRIC_L2, "angular": METRIC_ANGULAR, "l2sq": METRIC_L2SQ,
                   "cosine": METRIC_COSINE}

@@ -61,9 +61,14 @@ class PackedLists:
     def out(self):
         return self.ids, self.dists, self.ncand
 
-    def exchange_and_merge(self, group=None):
+    def exchange_and_merge(self, group=None, sqrt_after=False):
+        """ONE all-gather of the packed lists + the shard merge; sqrt_after: the lists hold squared L2
+        distances (FLAG_SQUARED_L2_OUT) and the root is taken on the merged result."""
         dist.all_gather_into_tensor(self.gathered, self.local, group=group)
-        return _native.merge_topk(self.g_dists, self.g_ids, self.g_ncand)
+        ids, dists, ncand = _native.merge_topk(self.g_dists, self.g_ids, self.g_ncand)
+        if sqrt_after:
+            dists.sqrt_()
+        return ids, dists, ncand
 
 
 class ShardedIndexer:
@@ -75,6 +80,7 @@ class ShardedIndexer:
         self.local = Indexer(hashing, local_vectors_gpu, distance_func, metric=metric,
                              id_offset=self.shard_lo)
         self._packed = {}  # (n_queries, k, stream) -> PackedLists of the eager path
+        self._squared = self.local._metric == _native.METRIC_L2  # shard lists carry squared L2 distances
 
     def _multi(self):
         return dist.is_initialized() and dist.get_world_size(self.group) > 1
@@ -87,8 +93,23 @@ class ShardedIndexer:
         packed = self._packed.get(key)
         if packed is None:  # exchange buffers are kept per batch shape (and stream), not allocated per call
             packed = self._packed[key] = PackedLists(key[0], k, dist.get_world_size(self.group), dev)
-        self.local.query_tensors(query_vectors, k, hash_times, probes, out=packed.out())
-        return packed.exchange_and_merge(self.group)
+        with self._shard_list_flags():
+            self.local.query_tensors(query_vectors, k, hash_times, probes, out=packed.out())
+        return packed.exchange_and_merge(self.group, sqrt_after=self._squared)
+
+    def _shard_list_flags(self):
+        """Context: this shard's lists are written for a cross-shard merge (squared L2 distances)."""
+        local, squared = self.local, self._squared
+
+        class _Ctx:
+            def __enter__(self_inner):
+                self_inner.saved = local.scan_flags
+                if squared:
+                    local.scan_flags |= _native.FLAG_SQUARED_L2_OUT
+
+            def __exit__(self_inner, *exc):
+                local.scan_flags = self_inner.saved
+        return _Ctx()
 
     def capture_query(self, n_queries, k=10, hash_times=10, shard_hashing=True, group=None):
         """The whole batch as ONE CUDA graph.  One rank: hash -> probe selection -> scan + top-k.  Several ranks:
@@ -161,9 +182,10 @@ class GraphedShardedQuery:
             else:
                 probes = local.hash_tensors(self.q, hash_times, workspace=self.workspace)
                 tau = None
-            local.query_tensors(self.q[:n_queries], k, hash_times, probes=probes, out=self.packed.out(),
-                                workspace=self.workspace, tau_seed=tau)
-            return self.packed.exchange_and_merge(group)
+            with sharded._shard_list_flags():
+                local.query_tensors(self.q[:n_queries], k, hash_times, probes=probes, out=self.packed.out(),
+                                    workspace=self.workspace, tau_seed=tau)
+            return self.packed.exchange_and_merge(group, sqrt_after=sharded._squared)
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

@@ -76,6 +76,46 @@ def test_sharded_search_equals_single_index(oracle):
         assert np.array_equal(o_ids, m_ids.cpu().numpy())
 
 
+@pytest.mark.parametrize("metric,d,k", [("l2", 64, 10), ("angular", 100, 10), ("l2", 200, 40)])
+def test_bounds_seeded_on_one_shard_serve_every_shard(monkeypatch, metric, d, k):
+    """nlsh_query_seed_tau / nlsh_query_scan_topk_seeded: a distance bound computed from a sample of ONE shard's
+    rows bounds the k-th best distance over the whole database, so every shard may filter with it (a row-sharded
+    search seeds each query on one rank only).  The merged result must not change - whichever shard seeds."""
+    from encoders import MultiLayerRelu
+    from nlsh import _native
+    from nlsh.hashings import MultivariateBernoulli
+    from nlsh.indexer import Indexer
+    from nlsh.parallel import shard_range
+    monkeypatch.setenv("NLSH_SCAN_IMPL", "tc")
+    torch.manual_seed(9)
+    n, hs, nq, p, G = 60000, 6, 700, 4, 4
+    X = mixture(n, d, 300, seed=31).cuda()
+    Q = (mixture(nq, d, 300, seed=31) + 0.1 * torch.randn(nq, d, generator=torch.Generator().manual_seed(3))).cuda()
+    hashing = MultivariateBernoulli(MultiLayerRelu(d, [48]), hs, None)
+    hashing.train_mode(False)
+    full = Indexer(hashing, X, None, metric=metric)
+    probes = full.hash_tensors(Q, p)
+    f_ids, f_d, f_n = full.query_tensors(Q, k=k, probes=probes)
+    shards = []
+    for r in range(G):
+        lo, hi = shard_range(n, r, G)
+        shards.append(Indexer(hashing, X[lo:hi], None, metric=metric, id_offset=lo))
+    for seeder in (0, G - 1):
+        tau = shards[seeder].seed_tau_tensors(Q, probes, k)
+        assert tau.shape == (nq,) and tau.dtype == torch.float32
+        # a valid bound: at least the exact k-th best distance over the whole database (squared for L2)
+        kth = f_d[:, k - 1] ** 2 if metric == "l2" else f_d[:, k - 1]
+        assert (tau >= kth).all()
+        for s in shards:  # shard lists carry squared L2 distances, the root follows the shard merge
+            s.scan_flags = _native.FLAG_SQUARED_L2_OUT if metric == "l2" else 0
+        parts = [s.query_tensors(Q, k=k, probes=probes, tau_seed=tau) for s in shards]
+        m_ids, m_d = _native.merge_topk(torch.stack([t[1] for t in parts]), torch.stack([t[0] for t in parts]))
+        if metric == "l2":
+            m_d = m_d.sqrt()
+        assert torch.equal(m_ids, f_ids) and torch.equal(m_d, f_d)
+        assert torch.equal(sum(t[2] for t in parts), f_n)
+
+
 @pytest.mark.parametrize("k", [1, 10, 33, 100, 128])
 def test_merge_kernel_against_oracle(oracle, k):
     from nlsh import _native
