@@ -993,6 +993,91 @@ __global__ void __launch_bounds__(32 * kMergeWarps)
   }
 }
 
+// The same merge with a whole block per query, for batches of few queries with long candidate buffers (config
+// 5: 1000 queries x ~1700 candidates, k = 100 - one warp per query would leave most of the GPU idle and walk
+// 50 batches of three-register-deep inserts in sequence): warp w takes the candidate batches w, w + 8, ...;
+// the warps' lists are merged through shared memory.  An overflowed query is re-scanned the same way.
+template <int KPL>
+__global__ void __launch_bounds__(32 * kMergeWarps)
+    merge_cands_block_kernel(const TcCand* __restrict__ cand, const int* __restrict__ cand_n, int cap,
+                             const float* __restrict__ qn, const float* __restrict__ xs,
+                             const int* __restrict__ row_ids, const int* __restrict__ probes,
+                             const int* __restrict__ offsets, int n_buckets, int p, int k, int d, int d_pad,
+                             int metric, int sqrt_out, long long n_queries, long long id_offset,
+                             const float* __restrict__ tau_g, long long* __restrict__ ids_out,
+                             float* __restrict__ dists_out, int* __restrict__ ncand_out,
+                             unsigned long long* __restrict__ stats) {
+  __shared__ float sh_d[kMergeWarps][32 * KPL];
+  __shared__ int sh_id[kMergeWarps][32 * KPL];
+  const int warp = threadIdx.x >> 5;
+  const int lane = lane_id();
+  const long long q = blockIdx.x;
+  if (q >= n_queries) return;
+  const int n = cand_n[q];
+  WarpTopK<KPL, int> top;
+  top.init(NLSH_ID_SENTINEL);
+  int ncand = 0;
+  if (n <= cap) {
+    const TcCand* cq = cand + (size_t)q * cap;
+    const float bound = tau_g[q];
+    for (int e0 = 32 * warp; e0 < n; e0 += 32 * kMergeWarps) {
+      const int e = e0 + lane;
+      TcCand c;
+      c.d = 0.f;
+      c.id = NLSH_ID_SENTINEL;
+      if (e < n) c = cq[e];
+      top.offer(c.d, c.id, e < n && c.d <= bound, k);
+    }
+  }
+  for (int j = 0; j < p; ++j) {
+    int b;
+    if (!probe_valid(probes, offsets, n_buckets, p, q * p + j, b)) continue;
+    const int r0 = offsets[b], r1 = offsets[b + 1];
+    ncand += r1 - r0;
+    if (n > cap) {  // block-uniform: the exact re-scan of an overflowed query
+      TcQueryGlobal qg;
+      qg.q = qn + (size_t)q * d_pad;
+      for (int base = r0 + 32 * warp; base < r1; base += 32 * kMergeWarps) {
+        const int row = base + lane;
+        float dist = 0.f;
+        int id = NLSH_ID_SENTINEL;
+        if (row < r1) {
+          dist = metric == NLSH_METRIC_L2
+                     ? tc_thread_distance<NLSH_METRIC_L2, 16>(xs + (size_t)row * d_pad, qg, d)
+                     : tc_thread_distance<NLSH_METRIC_ANGULAR, 16>(xs + (size_t)row * d_pad, qg, d);
+          id = row_ids[row];
+        }
+        top.offer(dist, id, row < r1, k);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    sh_d[warp][j * 32 + lane] = top.d[j];
+    sh_id[warp][j * 32 + lane] = top.id[j];
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  for (int w = 1; w < kMergeWarps; ++w) {
+#pragma unroll
+    for (int j = 0; j < KPL; ++j)
+      top.offer(sh_d[w][j * 32 + lane], sh_id[w][j * 32 + lane], sh_id[w][j * 32 + lane] != NLSH_ID_SENTINEL, k);
+  }
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    const int pos = j * 32 + lane;
+    if (pos < k) {
+      const int id = top.id[j];
+      ids_out[q * k + pos] = (id == NLSH_ID_SENTINEL) ? -1ll : (long long)id + id_offset;
+      dists_out[q * k + pos] = sqrt_out ? sqrtf(top.d[j]) : top.d[j];
+    }
+  }
+  if (lane == 0) {
+    if (ncand_out) ncand_out[q] = ncand;
+    if (stats != nullptr && n > cap) atomicAdd(stats + 5, 1ull);
+  }
+}
+
 // Cross-shard merge (after the NCCL all-gather): lists [n_lists, n_queries, k].
 template <int KPL>
 __global__ void __launch_bounds__(128)
@@ -1509,9 +1594,20 @@ extern "C" int nlsh_query_scan_topk_seeded(const float* xq, int64_t n_queries, i
     const unsigned mblocks = (unsigned)((n_queries + kMergeWarps - 1) / kMergeWarps);
 #define NLSH_MERGE_ARGS w.cand, w.cand_n, cap, w.qn, x_sorted, ids, probes, offsets, n_buckets, p, k, geom.d, geom.d_pad, \
                         metric, sqrt_scores, n_queries, id_offset, w.tau_g, reinterpret_cast<long long*>(ids_out), dists_out, ncand_out, stats
-    if (k <= 32) merge_cands_kernel<1><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
-    else if (k <= 64) merge_cands_kernel<2><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
-    else merge_cands_kernel<4><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
+    // a block per query when the buffers are long (k > 32) or the batch is too small to fill the GPU with warps
+    const bool per_block = k > 32 || n_queries <= 2048;
+    if (per_block) {
+      const unsigned qb = (unsigned)n_queries;
+      if (k <= 32) merge_cands_block_kernel<1><<<qb, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
+      else if (k <= 64) merge_cands_block_kernel<2><<<qb, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
+      else merge_cands_block_kernel<4><<<qb, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
+    } else if (k <= 32) {
+      merge_cands_kernel<1><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
+    } else if (k <= 64) {
+      merge_cands_kernel<2><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
+    } else {
+      merge_cands_kernel<4><<<mblocks, 32 * kMergeWarps, 0, st>>>(NLSH_MERGE_ARGS);
+    }
 #undef NLSH_MERGE_ARGS
     return nlsh_check_cuda(nlsh_post_launch(), "merge_cands_kernel launch");
   }

@@ -831,25 +831,29 @@ __global__ void __launch_bounds__(128, 5)
   }
 }
 
-// The same seed for wide rows (d_pad > 128) or k > 32: one warp per query, one sample row per lane and
-// step, every distance by one thread in the scorer's own arithmetic (tc_thread_distance), lists of up to
-// 128 entries.  The rows of a step are 32 different rows, so this kernel is latency bound; it only runs
-// where the pipelined 8-lanes-per-row kernel above does not apply.
+// The same seed for wide rows (d_pad > 128) or k > 32: a block of 8 warps per query, one sample row per lane
+// and step, every distance by one thread in the scorer's own arithmetic (tc_thread_distance), lists of up to
+// 128 entries per warp merged through shared memory.  The rows of a step are 32 different rows, so a warp is
+// latency bound: the 8 warps of a query take every eighth step.
+constexpr int kSeedWarps = 8;
+
 template <int METRIC, int KPL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * kSeedWarps)
     seed_tau_generic_kernel(const float* __restrict__ qn, const int* __restrict__ probes,
                             const int* __restrict__ offsets, const float* __restrict__ xs, int n_buckets, int p,
                             int d, int d_pad, int k, int seed_rows, int seed_div, long long n_queries,
                             float* __restrict__ tau_g, float* __restrict__ tau0) {
-  const long long q = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  __shared__ float sh_d[kSeedWarps][32 * KPL];
+  const long long q = blockIdx.x;
   if (q >= n_queries) return;
+  const int warp = threadIdx.x >> 5;
   const int lane = lane_id();
   TcQueryGlobal qg;
   qg.q = qn + (size_t)q * d_pad;
   WarpTopK<KPL, int> top;
   top.init(NLSH_ID_SENTINEL);
   int budget = -1, taken = 0;
-  for (int j = 0; j < p && budget != 0; ++j) {  // warp-uniform
+  for (int j = 0; j < p && budget != 0; ++j) {  // block-uniform
     const int b = probes[q * p + j];
     if (b < 0 || b >= n_buckets) continue;
     bool dup = false;
@@ -865,7 +869,7 @@ __global__ void __launch_bounds__(128)
       if (budget > kMaxSeedRows) budget = kMaxSeedRows;
     }
     const int n = size < budget ? size : budget;
-    for (int base = 0; base < n; base += 32) {
+    for (int base = 32 * warp; base < n; base += 32 * kSeedWarps) {
       const int r = base + lane;
       float dist = 0.f;
       if (r < n) dist = tc_thread_distance<METRIC, 8>(xs + (size_t)(r0 + r) * d_pad, qg, d);
@@ -874,10 +878,20 @@ __global__ void __launch_bounds__(128)
     budget -= n;
     taken += n;
   }
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) sh_d[warp][j * 32 + lane] = top.d[j];
+  __syncthreads();
+  if (warp != 0) return;
+  for (int w = 1; w < kSeedWarps; ++w) {
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const float v = sh_d[w][j * 32 + lane];
+      top.offer(v, (w << 16) | (j * 32 + lane), v < pos_inf(), k);  // only the k-th best VALUE matters here
+    }
+  }
   if (lane == 0) {
     float t = pos_inf();
-    // same arithmetic as the scorer: no inflation is needed, but the bound must not be below a distance
-    // the scorer would compute for the same row, which it is not (identical operations)
+    // same arithmetic as the scorer: a sample row's distance is bit-identical there, no inflation needed
     if (taken >= k && top.tau < pos_inf()) t = top.tau;
     tau_g[q] = t;
     tau0[q] = t;
@@ -947,7 +961,9 @@ int nlsh_scan_tc_seed(const float* qn, long long n_queries, const int* probes, i
   if (const char* env = getenv("NLSH_SCAN_SEED_DIV")) seed_div = atoi(env);
   if (seed_div < 1) seed_div = 1;
   if (seed_rows == 0) seed_div = 1 << 30;
-  if (seed_rows > 0 && seed_rows < 4 * k) seed_rows = 4 * k;  // a sample of at least a few times k rows
+  // a sample of at least a few times k rows; 8 k for long lists (config 5, k = 100, wide rows: every survivor
+  // costs the scorer 7.7 KB of reads - 400 sample rows 2.8 M survivors and a 6.4 ms scan, 800 rows 1.8 M and 4.7 ms)
+  if (seed_rows > 0 && seed_rows < (k > 32 ? 8 : 4) * k) seed_rows = (k > 32 ? 8 : 4) * k;
   const unsigned sb = (unsigned)((n_queries + 3) / 4);
 #define NLSH_SEED_ARGS qn, probes, offsets, xs, n_buckets, p, d, d_pad, k, seed_rows, seed_div, n_queries, tau_g, tau0
   if (d_pad <= kMaxKBlocks * kTcBK && k <= 32) {
@@ -956,13 +972,15 @@ int nlsh_scan_tc_seed(const float* qn, long long n_queries, const int* probes, i
     else
       seed_tau_kernel<NLSH_METRIC_ANGULAR><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
   } else if (metric == NLSH_METRIC_L2) {
-    if (k <= 32) seed_tau_generic_kernel<NLSH_METRIC_L2, 1><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
-    else if (k <= 64) seed_tau_generic_kernel<NLSH_METRIC_L2, 2><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
-    else seed_tau_generic_kernel<NLSH_METRIC_L2, 4><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
+    const unsigned gb = (unsigned)n_queries;
+    if (k <= 32) seed_tau_generic_kernel<NLSH_METRIC_L2, 1><<<gb, 32 * kSeedWarps, 0, st>>>(NLSH_SEED_ARGS);
+    else if (k <= 64) seed_tau_generic_kernel<NLSH_METRIC_L2, 2><<<gb, 32 * kSeedWarps, 0, st>>>(NLSH_SEED_ARGS);
+    else seed_tau_generic_kernel<NLSH_METRIC_L2, 4><<<gb, 32 * kSeedWarps, 0, st>>>(NLSH_SEED_ARGS);
   } else {
-    if (k <= 32) seed_tau_generic_kernel<NLSH_METRIC_ANGULAR, 1><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
-    else if (k <= 64) seed_tau_generic_kernel<NLSH_METRIC_ANGULAR, 2><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
-    else seed_tau_generic_kernel<NLSH_METRIC_ANGULAR, 4><<<sb, 128, 0, st>>>(NLSH_SEED_ARGS);
+    const unsigned gb = (unsigned)n_queries;
+    if (k <= 32) seed_tau_generic_kernel<NLSH_METRIC_ANGULAR, 1><<<gb, 32 * kSeedWarps, 0, st>>>(NLSH_SEED_ARGS);
+    else if (k <= 64) seed_tau_generic_kernel<NLSH_METRIC_ANGULAR, 2><<<gb, 32 * kSeedWarps, 0, st>>>(NLSH_SEED_ARGS);
+    else seed_tau_generic_kernel<NLSH_METRIC_ANGULAR, 4><<<gb, 32 * kSeedWarps, 0, st>>>(NLSH_SEED_ARGS);
   }
 #undef NLSH_SEED_ARGS
   return nlsh_check_cuda(nlsh_post_launch(), "seed_tau_kernel launch");
