@@ -92,7 +92,7 @@ int nlsh_pack_codes_host(const int32_t* bits, int64_t n, int64_t s, int64_t hs,
  * receives the pre-sigmoid outputs of the last layer; codes_out (device int32 [n], may be
  * NULL) receives the bucket code.  Thresholds reproduce torch's fp32 sigmoid / tanh
  * comparison bit-for-bit: sigmoid(l) > 0.5  <=>  l > 1.5*2^-24;  tanh(l)/2+0.5 > 0.5  <=>
- * l > 2^-24 (verified against torch 2.11 CPU, tests/test_oracle_hash.py).
+ * l > 2^-24 (verified against torch 2.11 CPU, tests/test_gpu_hash.py::test_threshold_dead_band_bit_exact and tests/test_oracle_golden.py).
  * ------------------------------------------------------------------------------------- */
 size_t nlsh_mlp_workspace_bytes(int64_t n, const nlsh_layer_t* layers, int32_t n_layers);
 int nlsh_mlp_hash_f32(const float* x, int64_t n, int32_t d, const nlsh_layer_t* layers,

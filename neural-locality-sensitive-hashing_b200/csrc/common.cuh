@@ -237,24 +237,37 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+constexpr uint64_t kMbarWatchdogNs = 30000000000ull;  // 30 s
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // try_wait suspends the thread in hardware (up to the hint) and returns early when the phase
-  // completes.  A wait that lasts 4 s means the pipeline is broken: trap (-> CUDA error on the
-  // host) instead of hanging the device.
+  // completes.  A wait that lasts kMbarWatchdogNs means the pipeline is broken: trap (-> CUDA error on
+  // the host) instead of hanging the device.  The bound is wall time (%globaltimer keeps running while
+  // the context is time-sliced out or replayed under a profiler), hence generous; -DNLSH_NO_WATCHDOG
+  // builds wait forever.
   if (mbar_try_wait(bar, parity)) return;
+#ifdef NLSH_NO_WATCHDOG
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#else
   const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (global_timer_ns() - t0 > 4000000000ull) __trap();
+    if (global_timer_ns() - t0 > kMbarWatchdogNs) __trap();
   }
+#endif
 }
 // Polling variant for deep pipelines (scan_tc.cu: five roles hand tiles to each other, so the
 // wake-up latency of a long suspended wait would be paid several times per tile).
 __device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait_short(bar, parity)) return;
+#ifdef NLSH_NO_WATCHDOG
+  while (!mbar_try_wait_short(bar, parity)) {
+  }
+#else
   const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait_short(bar, parity)) {
-    if (global_timer_ns() - t0 > 4000000000ull) __trap();
+    if (global_timer_ns() - t0 > kMbarWatchdogNs) __trap();
   }
+#endif
 }
 // global -> shared bulk copy (SASS UBLKCP), completion counted in bytes on `bar`.
 // dst/src 16-byte aligned, bytes a multiple of 16.

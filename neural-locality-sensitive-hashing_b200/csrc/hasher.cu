@@ -194,7 +194,7 @@ __global__ void codes_kernel(const float* __restrict__ logits, long long n, int 
 // is identical to the full enumeration of oracle.topp_probes.
 template <int KPL>
 __global__ void __launch_bounds__(128)
-    probes_bernoulli_kernel(const float* __restrict__ logits, long long n, int hs, int head, int p,
+    probes_topp_kernel(const float* __restrict__ logits, long long n, int hs, int head, int p,
                             int* __restrict__ probes) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -232,22 +232,22 @@ __global__ void __launch_bounds__(128)
   const int n_masks = 1 << n_sel;
   for (int m0 = 0; m0 < n_masks; m0 += 32) {
     const int mc = m0 + lane;  // compact mask over the selected bits (ascending position)
+    // cost of the mask = sum of its bits' costs, added from the highest position down (the order of the full
+    // enumeration in oracle.topp_probes, so equal sums are bit-equal); bit j of mc = j-th selected position
     float cost = 0.f;
     int full = 0;
-#pragma unroll
-    for (int i = 0; i < NLSH_MAX_HASH_BITS; ++i) {
-      if (i < hs) {
-        const int pos = hs - 1 - i;
-        if ((sel >> pos) & 1u) {
-          const int j = __popc(sel & ((1u << pos) - 1u));
-          if ((mc >> j) & 1) {
-            cost = __fadd_rn(cost, a[i]);
-            full |= 1 << pos;
-          }
-        }
+    for (int j = n_sel - 1; j >= 0; --j) {  // warp-uniform
+      const int pos = __fns(sel, 0, j + 1);
+      const float c = __shfl_sync(NLSH_FULL_MASK, my_cost, pos);
+      if ((mc >> j) & 1) {
+        cost = __fadd_rn(cost, c);
+        full |= 1 << pos;
       }
     }
-    top.offer(cost, full, mc < n_masks, p);
+    if (m0 == 0)  // the first 32 masks: one bitonic sort instead of p inserts into the empty list
+      top.seed32(cost, full, mc < n_masks, NLSH_ID_SENTINEL, p);
+    else
+      top.offer(cost, full, mc < n_masks, p);
   }
 #pragma unroll
   for (int j = 0; j < KPL; ++j) {
@@ -544,11 +544,11 @@ extern "C" int nlsh_topp_probes(const float* logits, int64_t n, int32_t hash_siz
       probes_softmax_kernel<4><<<blocks, 128, 0, st>>>(logits, n, hash_size, p, probes_out);
   } else {
     if (kpl == 1)
-      probes_bernoulli_kernel<1><<<blocks, 128, 0, st>>>(logits, n, hash_size, head, p, probes_out);
+      probes_topp_kernel<1><<<blocks, 128, 0, st>>>(logits, n, hash_size, head, p, probes_out);
     else if (kpl == 2)
-      probes_bernoulli_kernel<2><<<blocks, 128, 0, st>>>(logits, n, hash_size, head, p, probes_out);
+      probes_topp_kernel<2><<<blocks, 128, 0, st>>>(logits, n, hash_size, head, p, probes_out);
     else
-      probes_bernoulli_kernel<4><<<blocks, 128, 0, st>>>(logits, n, hash_size, head, p, probes_out);
+      probes_topp_kernel<4><<<blocks, 128, 0, st>>>(logits, n, hash_size, head, p, probes_out);
   }
   return nlsh_check_cuda(nlsh_post_launch(), "probes kernel launch");
 }
