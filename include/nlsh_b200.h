@@ -114,6 +114,17 @@ int nlsh_codes_from_logits(const float* logits, int64_t n, int32_t hash_size, in
 int nlsh_topp_probes(const float* logits, int64_t n, int32_t hash_size, int32_t head,
                      int32_t p, int32_t* probes_out, void* stream);
 
+/* Sampled multi-probe, the reference's own semantics (hashings.py:77-81: n - 1 draws of
+ * torch.distributions.Bernoulli(probs) next to the hard code): probes_out[i, 0] is the hard code,
+ * probes_out[i, j >= 1] the packed code of an independent draw, bit b set with probability
+ * sigmoid(logit_b) (tanh head: tanh(logit_b) / 2 + 0.5).  Uniforms come from Philox-4x32-10 keyed by
+ * `seed` with counter (row, j, b / 4): the same (seed, logits) always gives the same probes; rows may
+ * repeat a code (the reference collects them into a set, utils.pyx:18-32; the scan ignores repeats).
+ * The stream of torch's own sampler is not reproduced (it depends on torch's launch geometry): parity
+ * is in distribution, and reference-sampled sets can be replayed through `probes` of the scan. */
+int nlsh_sample_probes(const float* logits, int64_t n, int32_t hash_size, int32_t head,
+                       int32_t p, uint64_t seed, int32_t* probes_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Index build: codes -> CSR bucket layout + bucket-contiguous copy of the vectors.
  * Replaces build_index (nlsh/indexer.py:6-24) for single-code rows (hash_times = 1, the

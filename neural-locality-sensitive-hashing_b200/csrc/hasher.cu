@@ -519,6 +519,73 @@ extern "C" int nlsh_mlp_hash_f32(const float* x, int64_t n, int32_t d, const nls
   return NLSH_OK;
 }
 
+// ---- sampled multi-probe (hashings.py:77-81) ------------------------------------------------
+// Philox-4x32-10 (Salmon et al. 2011), the counter-based generator torch's CUDA sampler is built on: one
+// call = four 32-bit words from (counter, key); no state, so a (row, probe, bit) triple always gets the
+// same uniform for a given seed.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// probes[i, 0] = hard code (`dist.probs > 0.5`), probes[i, j] for j >= 1 = packed code of one draw of
+// Bernoulli(probs) per bit, bit b set iff u(i, j, b) < prob_b with u = (word >> 8) * 2^-24 in [0, 1).
+// One thread per (row, probe).
+__global__ void __launch_bounds__(256)
+    probes_sample_kernel(const float* __restrict__ logits, long long n, int hs, int head, int p,
+                         unsigned long long seed, int* __restrict__ probes) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * p) return;
+  const long long row = t / p;
+  const int j = (int)(t - row * p);
+  const float thr = head == NLSH_HEAD_TANH ? 5.9604644775390625e-08f : 8.940696716308594e-08f;
+  const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+  int code = 0;
+  for (int b0 = 0; b0 < hs; b0 += 4) {
+    const uint4 w = philox4x32_10(make_uint4((unsigned)row, (unsigned)(row >> 32), (unsigned)j, (unsigned)(b0 >> 2)), key);
+    const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (b0 + e < hs) {
+        const float l = logits[row * hs + b0 + e];
+        int bit;
+        if (j == 0) {
+          bit = l > thr ? 1 : 0;  // the reference's fp32 `probs > 0.5`, as in codes_kernel
+        } else {
+          const float prob = head == NLSH_HEAD_TANH ? tanhf(l) * 0.5f + 0.5f : 1.0f / (1.0f + expf(-l));
+          const float u = (float)(ws[e] >> 8) * 5.9604644775390625e-08f;
+          bit = u < prob ? 1 : 0;
+        }
+        code = (code << 1) | bit;  // MSB first (utils.pyx:12-14)
+      }
+    }
+  }
+  probes[t] = code;
+}
+
+extern "C" int nlsh_sample_probes(const float* logits, int64_t n, int32_t hash_size, int32_t head,
+                                  int32_t p, uint64_t seed, int32_t* probes_out, void* stream) {
+  NLSH_REQUIRE(n >= 0 && hash_size >= 1 && hash_size <= NLSH_MAX_HASH_BITS,
+               "sample probes: bad shape n=%lld hash_size=%d", (long long)n, hash_size);
+  NLSH_REQUIRE(p >= 1 && p <= 1024, "sample probes: p=%d outside [1, 1024]", p);
+  NLSH_REQUIRE(head == NLSH_HEAD_SIGMOID || head == NLSH_HEAD_TANH,
+               "sample probes: head %d has no Bernoulli sampling (hashings.py:66-92 is the bit hasher)", head);
+  if (n == 0) return NLSH_OK;
+  NLSH_REQUIRE(logits && probes_out, "sample probes: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = (long long)n * p;
+  probes_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(logits, n, hash_size, head, p, seed,
+                                                                       probes_out);
+  return nlsh_check_cuda(nlsh_post_launch(), "probes_sample_kernel launch");
+}
+
 extern "C" int nlsh_topp_probes(const float* logits, int64_t n, int32_t hash_size, int32_t head,
                                 int32_t p, int32_t* probes_out, void* stream) {
   NLSH_REQUIRE(n >= 0 && hash_size >= 1, "probes: bad shape n=%lld hash_size=%d", (long long)n,

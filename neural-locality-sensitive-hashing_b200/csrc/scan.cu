@@ -960,8 +960,8 @@ __global__ void __launch_bounds__(32 * kMergeWarps)
         int id = NLSH_ID_SENTINEL;
         if (row < r1) {
           dist = metric == NLSH_METRIC_L2
-                     ? tc_thread_distance<NLSH_METRIC_L2, 16>(xs + (size_t)row * d_pad, qg, d)
-                     : tc_thread_distance<NLSH_METRIC_ANGULAR, 16>(xs + (size_t)row * d_pad, qg, d);
+                     ? tc_thread_distance<NLSH_METRIC_L2, 16, false>(xs + (size_t)row * d_pad, qg, d)
+                     : tc_thread_distance<NLSH_METRIC_ANGULAR, 16, false>(xs + (size_t)row * d_pad, qg, d);
           id = row_ids[row];
         }
         top.offer(dist, id, row < r1, k);
@@ -1043,8 +1043,8 @@ __global__ void __launch_bounds__(32 * kMergeWarps)
         int id = NLSH_ID_SENTINEL;
         if (row < r1) {
           dist = metric == NLSH_METRIC_L2
-                     ? tc_thread_distance<NLSH_METRIC_L2, 16>(xs + (size_t)row * d_pad, qg, d)
-                     : tc_thread_distance<NLSH_METRIC_ANGULAR, 16>(xs + (size_t)row * d_pad, qg, d);
+                     ? tc_thread_distance<NLSH_METRIC_L2, 16, false>(xs + (size_t)row * d_pad, qg, d)
+                     : tc_thread_distance<NLSH_METRIC_ANGULAR, 16, false>(xs + (size_t)row * d_pad, qg, d);
           id = row_ids[row];
         }
         top.offer(dist, id, row < r1, k);

@@ -74,10 +74,38 @@ namespace {
 #define MBAR_WAIT mbar_wait_poll
 #endif
 
+// -DNLSH_TC_ROLE_STATS (the `stats` target of the Makefile, lib/libnlsh_b200_stats.so): cycles every role
+// spends in each of its waits, summed over all CTAs into stats[6..] (scripts/dbg_tc_roles.py prints them).
+#ifdef NLSH_TC_ROLE_STATS
+#define ROLE_T0() const long long role_t0 = clock64(); long long role_w[4] = {0, 0, 0, 0}
+#define ROLE_WAIT(slot, bar, par)        \
+  do {                                   \
+    const long long t_ = clock64();      \
+    MBAR_WAIT(bar, par);                 \
+    role_w[slot] += clock64() - t_;      \
+  } while (0)
+#define ROLE_TIC() const long long role_tic = clock64()
+#define ROLE_TOC(slot) role_w[slot] += clock64() - role_tic
+#define ROLE_REPORT(base)                                                                   \
+  do {                                                                                      \
+    if (a.stats != nullptr && lane == 0) {                                                  \
+      for (int i_ = 0; i_ < 4; ++i_) atomicAdd(a.stats + (base) + i_, (unsigned long long)role_w[i_]); \
+      atomicAdd(a.stats + (base) + 4, (unsigned long long)(clock64() - role_t0));           \
+    }                                                                                       \
+  } while (0)
+#else
+#define ROLE_T0()
+#define ROLE_WAIT(slot, bar, par) MBAR_WAIT(bar, par)
+#define ROLE_TIC()
+#define ROLE_TOC(slot)
+#define ROLE_REPORT(base)
+#endif
+
 constexpr int kGroups = 2;                      // filter groups (tiles alternate between them)
 constexpr int kFilterWarps = 4 * kGroups;       // one per TMEM lane quarter and group
 constexpr int kTile = 128;                      // rows per tile = UMMA M
-constexpr int kThreads = 64 + 32 * kFilterWarps;  // 320
+constexpr int kStreamWarp = 2 + kFilterWarps;    // warp 10: streams the row tiles
+constexpr int kThreads = 96 + 32 * kFilterWarps;  // 352
 constexpr int kTmemCols = 512;                  // TMEM accumulator ring: 16 sets of 32 columns or 4 sets of 128
 constexpr int kMaxAccSets = 16;
 constexpr uint32_t kSlotBytes = kTile * kTcBK * sizeof(float);   // 16 KB: one K block of a row tile
@@ -85,7 +113,7 @@ constexpr uint32_t kSubBoxBytes = 32 * kTcBK * sizeof(float);    // 4 KB: a 32-r
 constexpr uint32_t kQBoxBytes = kTcNQ * kTcBK * sizeof(float);   // 4 KB: one K block of the queries
 constexpr int kMaxSlots = 16;
 constexpr int kMetaFloats = kTile + 4;          // a tile's row norms, from the 16-byte boundary below its first row
-constexpr uint32_t kMetaBytes = 640;            // kMetaFloats * 4 rounded up to 128
+constexpr uint32_t kMetaBytes = 528;            // kMetaFloats * 4 (a multiple of 16: bulk-copy destination)
 constexpr int kMetaBufs = 16;                   // row-norm ring depth (tiles)
 constexpr int kItemBufs = 4;                    // item ring depth: buckets of a few tiles are shorter than the
                                                 // pipeline, so several items must be in flight
@@ -122,6 +150,10 @@ struct TcQueryShared {
   __device__ __forceinline__ float4 load4(int v) const {
     return *reinterpret_cast<const float4*>(base + (v >> 3) * kQBoxBytes + (((v & 7) ^ sw) << 4));
   }
+  __device__ __forceinline__ void load8(int v, float4& a, float4& b) const {
+    a = load4(v);
+    b = load4(v + 1);
+  }
   __device__ __forceinline__ float load1(int c) const {
     const int v = c >> 2;
     return *reinterpret_cast<const float*>(base + (v >> 3) * kQBoxBytes + (((v & 7) ^ sw) << 4) + ((c & 3) << 2));
@@ -133,14 +165,18 @@ struct SmemLayout {
   unsigned char* qbuf;    // [kItemBufs][kblocks][NQ * 128 bytes] (not WIDE)
   unsigned char* meta;    // [kMetaBufs][kMetaBytes] row norms
   float* thr_s;           // [kItemBufs][NQ] filter thresholds
+  float* tau_s;           // [kItemBufs][NQ] the bound each threshold was made from (planner only)
+  float* qn2_s;           // [kItemBufs][NQ] |q|^2 (planner only)
   int* qi_s;              // [kItemBufs][NQ] query indices (-1 unused)
   TcItem* itm;            // [kItemBufs]
   int* wq_row;            // [kFilterWarps][kQueueCap] survivor queues: row of x_sorted
-  int* wq_meta;           // [kFilterWarps][kQueueCap] (item slot << 8) | query j
+  int* wq_meta;           // [kFilterWarps][kQueueCap] pair index (QGLOBAL) or (item slot << 8) | query j
+  int* wq_qi;             // [kFilterWarps][kQueueCap] query index
   uint64_t* full_bar;     // [kMaxSlots]
   uint64_t* empty_bar;    // [kMaxSlots]
-  uint64_t* q_full;       // [kItemBufs]
+  uint64_t* q_full;       // [kItemBufs] item state + queries in shared memory
   uint64_t* q_empty;      // [kItemBufs]
+  uint64_t* itm_full;     // [kItemBufs] item state alone (what the tile streamer needs)
   uint64_t* acc_full;     // [kMaxAccSets]
   uint64_t* acc_empty;    // [kMaxAccSets]
   uint64_t* meta_full;    // [kMetaBufs]
@@ -150,9 +186,9 @@ struct SmemLayout {
 
 __host__ __device__ inline size_t smem_fixed_bytes(int kblocks, bool wide, int nq) {
   return (wide ? 0 : (size_t)kItemBufs * kblocks * nq * 128) + (size_t)kMetaBufs * kMetaBytes +
-         2 * kItemBufs * nq * sizeof(float) + kItemBufs * sizeof(TcItem) +
-         2 * kFilterWarps * kQueueCap * sizeof(int) +
-         (2 * kMaxSlots + 2 * kItemBufs + 2 * kMaxAccSets + 2 * kMetaBufs) * sizeof(uint64_t) + 16;
+         4 * kItemBufs * nq * sizeof(float) + kItemBufs * sizeof(TcItem) +
+         3 * kFilterWarps * kQueueCap * sizeof(int) +
+         (2 * kMaxSlots + 3 * kItemBufs + 2 * kMaxAccSets + 2 * kMetaBufs) * sizeof(uint64_t) + 16;
 }
 
 __device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int n_slots, int kblocks, bool wide, int nq) {
@@ -161,15 +197,19 @@ __device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int n_slot
   s.qbuf = s.slots + (size_t)n_slots * (kSlotBytes + (wide ? nq * 128u : 0u));
   s.meta = s.qbuf + (wide ? 0 : (size_t)kItemBufs * kblocks * nq * 128);
   s.thr_s = reinterpret_cast<float*>(s.meta + (size_t)kMetaBufs * kMetaBytes);
-  s.qi_s = reinterpret_cast<int*>(s.thr_s + kItemBufs * nq);
+  s.tau_s = s.thr_s + kItemBufs * nq;
+  s.qn2_s = s.tau_s + kItemBufs * nq;
+  s.qi_s = reinterpret_cast<int*>(s.qn2_s + kItemBufs * nq);
   s.itm = reinterpret_cast<TcItem*>(s.qi_s + kItemBufs * nq);
   s.wq_row = reinterpret_cast<int*>(s.itm + kItemBufs);
   s.wq_meta = s.wq_row + kFilterWarps * kQueueCap;
-  s.full_bar = reinterpret_cast<uint64_t*>(s.wq_meta + kFilterWarps * kQueueCap);
+  s.wq_qi = s.wq_meta + kFilterWarps * kQueueCap;
+  s.full_bar = reinterpret_cast<uint64_t*>(s.wq_qi + kFilterWarps * kQueueCap);
   s.empty_bar = s.full_bar + kMaxSlots;
   s.q_full = s.empty_bar + kMaxSlots;
   s.q_empty = s.q_full + kItemBufs;
-  s.acc_full = s.q_empty + kItemBufs;
+  s.itm_full = s.q_empty + kItemBufs;
+  s.acc_full = s.itm_full + kItemBufs;
   s.acc_empty = s.acc_full + kMaxAccSets;
   s.meta_full = s.acc_empty + kMaxAccSets;
   s.meta_empty = s.meta_full + kMetaBufs;
@@ -211,34 +251,67 @@ struct ScoreCtx {
 #ifndef NLSH_SCORE_INLINE  // A/B: -DNLSH_SCORE_INLINE=__noinline__
 #define NLSH_SCORE_INLINE __forceinline__
 #endif
-template <int METRIC, bool QGLOBAL>
-__device__ NLSH_SCORE_INLINE void score_batch(const ScoreCtx a, const int* q_row, const int* q_meta, unsigned head,
-                                         int n, int lane, unsigned& n_appended) {
+#ifndef NLSH_TC_QS_BATCH  // row float4s in flight per lane when the query is read from shared memory
+#define NLSH_TC_QS_BATCH 8
+#endif
+template <int METRIC, bool QGLOBAL, bool V8>
+__device__ NLSH_SCORE_INLINE void score_batch(const ScoreCtx a, const int* q_row, const int* q_meta, const int* q_qi,
+                                         unsigned head, int n, int lane, unsigned& n_appended) {
   if (lane < n) {
     const unsigned e = (head + (unsigned)lane) & (kQueueCap - 1);
     const int row = q_row[e];
     const int meta = q_meta[e];
+    const int qi = q_qi[e];
+    // what depends only on (row, query) is requested before the row is read: one L2 round trip for a batch's
+    // loads, one more for the append and the ladder counts of the lanes that found a candidate
     const int id = __ldg(a.ids + row);
-    int qi;
+    // the bound is read fresh: other items of the same query may have lowered it since this item was picked up
+    const float ext = __ldcg(a.tau_g + qi);
+    const float t0 = a.ladder != nullptr ? __ldg(a.tau0 + qi) : 0.f;
     float dist;
     if (QGLOBAL) {
-      qi = __ldg(a.pq + meta);
       TcQueryGlobal q;
       q.q = a.qs + (size_t)meta * a.d_pad;
-      dist = tc_thread_distance<METRIC, 16>(a.xs + (size_t)row * a.d_pad, q, a.d);
+      dist = tc_thread_distance<METRIC, 16, V8>(a.xs + (size_t)row * a.d_pad, q, a.d);
     } else {
       const int islot = meta >> 8, j = meta & 255;
-      qi = a.qi_s[islot * kTcNQ + j];
       TcQueryShared q;
       q.base = a.qbuf + (size_t)islot * a.kblocks * kQBoxBytes + j * 128;
       q.sw = j & 7;
-      dist = tc_thread_distance<METRIC, 16>(a.xs + (size_t)row * a.d_pad, q, a.d);
+      dist = tc_thread_distance<METRIC, NLSH_TC_QS_BATCH, V8>(a.xs + (size_t)row * a.d_pad, q, a.d);
     }
-    // the bound is read fresh: other items of the same query may have lowered it since this item was
-    // picked up
-    const float ext = __ldcg(a.tau_g + qi);
     if (dist <= ext) {
-      const int pos = atomicAdd(a.cand_n + qi, 1);
+      const int pos = atomicAdd(a.cand_n + qi, 1);  // its round trip overlaps the ladder's
+      if (a.ladder != nullptr && t0 > 0.f && t0 < pos_inf()) {
+        // threshold ladder: count this candidate at the tightest level it satisfies, then look for the
+        // tightest level whose cumulative count reaches k (read after the add: the lanes of a batch often
+        // score candidates of the same query, and each should see the others' counts)
+        int l = (int)((1.0f - dist / t0) * (float)kTcLadderDen);
+        l = l < 0 ? 0 : (l > kTcLadder - 1 ? kTcLadder - 1 : l);
+        while (l > 0 && !(dist <= t0 * (1.0f - (float)l * (1.0f / kTcLadderDen)))) --l;
+        int* lad = a.ladder + (size_t)qi * kTcLadder;
+        atomicAdd(lad + l, 1);
+        if (l > 0) {
+          int cnt[kTcLadder];
+#pragma unroll
+          for (int m4 = 0; m4 < kTcLadder; m4 += 4) {
+            const int4 c4 = __ldcg(reinterpret_cast<const int4*>(lad + m4));
+            cnt[m4] = c4.x;
+            cnt[m4 + 1] = c4.y;
+            cnt[m4 + 2] = c4.z;
+            cnt[m4 + 3] = c4.w;
+          }
+          int cum = 0, best = 0;
+#pragma unroll
+          for (int m = kTcLadder - 1; m >= 1; --m) {
+            cum += cnt[m];
+            if (best == 0 && cum >= a.k) best = m;
+          }
+          if (best > 0)
+            atomicMin(reinterpret_cast<int*>(a.tau_g + qi),
+                      __float_as_int(t0 * (1.0f - (float)best * (1.0f / kTcLadderDen))));
+        }
+      }
       if (pos < a.cap) {
         TcCand c;
         c.d = dist;
@@ -246,44 +319,12 @@ __device__ NLSH_SCORE_INLINE void score_batch(const ScoreCtx a, const int* q_row
         a.cand[(size_t)qi * a.cap + pos] = c;
       }
       ++n_appended;
-      if (a.ladder != nullptr) {
-        // threshold ladder: count this candidate at the tightest level it satisfies, then look for the
-        // tightest level whose cumulative count reaches k
-        const float t0 = __ldg(a.tau0 + qi);
-        if (t0 > 0.f && t0 < pos_inf()) {
-          int l = (int)((1.0f - dist / t0) * (float)kTcLadderDen);
-          l = l < 0 ? 0 : (l > kTcLadder - 1 ? kTcLadder - 1 : l);
-          while (l > 0 && !(dist <= t0 * (1.0f - (float)l * (1.0f / kTcLadderDen)))) --l;
-          int* lad = a.ladder + (size_t)qi * kTcLadder;
-          atomicAdd(lad + l, 1);
-          if (l > 0) {
-            int cnt[kTcLadder];
-#pragma unroll
-            for (int m4 = 0; m4 < kTcLadder; m4 += 4) {
-              const int4 c4 = __ldcg(reinterpret_cast<const int4*>(lad + m4));
-              cnt[m4] = c4.x;
-              cnt[m4 + 1] = c4.y;
-              cnt[m4 + 2] = c4.z;
-              cnt[m4 + 3] = c4.w;
-            }
-            int cum = 0, best = 0;
-#pragma unroll
-            for (int m = kTcLadder - 1; m >= 1; --m) {
-              cum += cnt[m];
-              if (best == 0 && cum >= a.k) best = m;
-            }
-            if (best > 0)
-              atomicMin(reinterpret_cast<int*>(a.tau_g + qi),
-                        __float_as_int(t0 * (1.0f - (float)best * (1.0f / kTcLadderDen))));
-          }
-        }
-      }
     }
   }
   __syncwarp();
 }
 
-template <int METRIC, int NQ, bool WIDE, bool QGLOBAL>
+template <int METRIC, int NQ, bool WIDE, bool QGLOBAL, bool V8>
 __global__ void __launch_bounds__(kThreads, 1)
     scan_tc_kernel(const TcScanArgs a, const __grid_constant__ CUtensorMap map_x,
                    const __grid_constant__ CUtensorMap map_x32, const __grid_constant__ CUtensorMap map_q) {
@@ -316,6 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int i = 0; i < kItemBufs; ++i) {
       mbar_init(&s.q_full[i], 1);
       mbar_init(&s.q_empty[i], kFilterWarps);
+      mbar_init(&s.itm_full[i], 1);
     }
     for (int i = 0; i < kSets; ++i) {
       mbar_init(&s.acc_full[i], 1);
@@ -330,13 +372,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *s.tmem_slot;
 
   if (warp == 0) {
-    // =================================== producer =========================================
+    // =================================== planner ==========================================
+    ROLE_T0();
     int total = *a.n_items;
     if (total > a.max_items) total = a.max_items;
-    auto next_index = [&]() {
+    // lane 0 draws the next item index; the value is broadcast one iteration later, so the atomic's round
+    // trip is never waited for (inline PTX: the compiler turns atomicAdd on a uniform address into a
+    // warp-aggregated atomic with a shuffle right behind it)
+    auto claim = [&]() {
       int v = 0;
-      if (lane == 0) v = atomicAdd(a.item_counter, 1);
-      return __shfl_sync(NLSH_FULL_MASK, v, 0);
+      if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(a.item_counter) : "memory");
+      return v;
     };
     auto load_rec = [&](int idx) {
       TcItem r;
@@ -363,47 +409,90 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
       for (int c = 0; c < kCh; ++c) tau[c] = h.qi[c] >= 0 ? __ldcg(a.tau_g + h.qi[c]) : neg_inf();
     };
+    // Threshold refresh: other items of the same queries (on any SM) lower tau_g while the published items
+    // are streamed.  Whenever the planner has to wait for an item slot it re-reads tau_g for the queries of
+    // every published slot and rewrites the thresholds that got lower (the filter may read the old or the
+    // new value: both are upper bounds; the planner is the only writer of the item slots).
+    auto refresh = [&](int n_live) {
+#ifndef NLSH_NO_REFRESH  // A/B: -DNLSH_NO_REFRESH
+      float t[kItemBufs][kCh];
+#pragma unroll
+      for (int b = 0; b < kItemBufs; ++b) {
+#pragma unroll
+        for (int c = 0; c < kCh; ++c) {
+          const int qi = b < n_live ? s.qi_s[b * NQ + 32 * c + lane] : -1;
+          t[b][c] = qi >= 0 ? __ldcg(a.tau_g + qi) : pos_inf();
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < kItemBufs; ++b) {
+#pragma unroll
+        for (int c = 0; c < kCh; ++c) {
+          const int e = b * NQ + 32 * c + lane;
+          if (t[b][c] < s.tau_s[e]) {
+            s.tau_s[e] = t[b][c];
+            s.thr_s[e] = make_thr<METRIC>(t[b][c], s.qn2_s[e], a.l2_slack);
+          }
+        }
+      }
+      __syncwarp();
+#endif
+    };
     // look-ahead pipeline: index of item i+3, record of i+2, pair state of i+1, tau_g of i
-    int idx3 = next_index();
+    int idx3 = __shfl_sync(NLSH_FULL_MASK, claim(), 0);
     Ahead<kCh> cur, nx1, nx2;
     cur.rec = load_rec(idx3);
-    idx3 = next_index();
+    idx3 = __shfl_sync(NLSH_FULL_MASK, claim(), 0);
     nx1.rec = load_rec(idx3);
-    idx3 = next_index();
+    idx3 = __shfl_sync(NLSH_FULL_MASK, claim(), 0);
     nx2.rec = load_rec(idx3);
-    idx3 = next_index();
+    int pend = claim();
     load_pair(cur);
     load_pair(nx1);
     float tau_cur[kCh], tau_nx1[kCh];
     load_tau(cur, tau_cur);
-    unsigned ring = 0, icount = 0, tcount = 0;
+    unsigned icount = 0;
     while (true) {
-      // issue the look-ahead loads first: they complete while this item's tiles are streamed
+      // issue the look-ahead loads first: they complete while the planner waits for the item slot
+      idx3 = __shfl_sync(NLSH_FULL_MASK, pend, 0);
       const TcItem rec3 = load_rec(idx3);                      // item i+3
-      idx3 = next_index();                                     // index of item i+4
+      pend = claim();                                          // index of item i+4
       load_pair(nx2);                                          // item i+2 (its record arrived last iteration)
       load_tau(nx1, tau_nx1);                                  // item i+1
 
       const int islot = (int)(icount % kItemBufs);
-      MBAR_WAIT(&s.q_empty[islot], ((icount / kItemBufs) & 1u) ^ 1u);
+      {
+        const unsigned par = ((icount / kItemBufs) & 1u) ^ 1u;
+        ROLE_TIC();
+        while (!mbar_try_wait_short(&s.q_empty[islot], par)) refresh(icount < kItemBufs ? (int)icount : kItemBufs);
+        ROLE_TOC(0);
+      }
       const TcItem rec = cur.rec;
       if (rec.nq == 0) {
         if (lane == 0) {
           s.itm[islot].nq = 0;  // end of work
+          mbar_arrive(&s.itm_full[islot]);
           mbar_arrive(&s.q_full[islot]);
         }
         break;
       }
 #pragma unroll
       for (int c = 0; c < kCh; ++c) {  // lane l: state of the item's query 32 c + l
-        float th = neg_inf();
-        if (32 * c + lane < rec.nq) th = make_thr<METRIC>(tau_cur[c], cur.qn2[c], a.l2_slack);
-        s.thr_s[islot * NQ + 32 * c + lane] = th;
-        s.qi_s[islot * NQ + 32 * c + lane] = cur.qi[c];
+        float th = neg_inf(), tau = neg_inf();
+        if (32 * c + lane < rec.nq) {
+          tau = tau_cur[c];
+          th = make_thr<METRIC>(tau, cur.qn2[c], a.l2_slack);
+        }
+        const int e = islot * NQ + 32 * c + lane;
+        s.thr_s[e] = th;
+        s.tau_s[e] = tau;
+        s.qn2_s[e] = cur.qn2[c];
+        s.qi_s[e] = cur.qi[c];
       }
       if (lane == 0) s.itm[islot] = rec;
       __syncwarp();
       if (lane == 0) {
+        mbar_arrive(&s.itm_full[islot]);  // the streamer starts on the row tiles
         if (WIDE) {
           mbar_arrive(&s.q_full[islot]);  // only the item's state: the queries travel with the row tiles
         } else {
@@ -413,41 +502,39 @@ __global__ void __launch_bounds__(kThreads, 1)
             tma_load_2d(qdst + kb * kQBytes, &map_q, kb * kTcBK, rec.pair_base, &s.q_full[islot]);
         }
       }
-      const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
-      float tau_new[kCh];
+      __syncwarp();
+      ++icount;
+      cur = nx1;
 #pragma unroll
-      for (int c = 0; c < kCh; ++c) tau_new[c] = tau_cur[c];
+      for (int c = 0; c < kCh; ++c) tau_cur[c] = tau_nx1[c];
+      nx1 = nx2;
+      nx2.rec = rec3;
+    }
+    ROLE_REPORT(6);  // wait q_empty (threshold refresh rounds included), -, -, -, total
+  } else if (warp == kStreamWarp) {
+    // =================================== tile streamer ====================================
+    if (lane == 0) {
+      ROLE_T0();
+      unsigned sl = 0, sl_par = 0;  // slot ring position and the parity of its current round
+      unsigned icount = 0, tcount = 0;
+      const long long n_rows4 = a.n_rows & ~3ll;
+      while (true) {
+        const int islot = (int)(icount % kItemBufs);
+        ROLE_WAIT(0, &s.itm_full[islot], (icount / kItemBufs) & 1u);
+        const TcItem rec = s.itm[islot];
+        if (rec.nq == 0) break;
+        const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
 #pragma unroll 1
-      for (int t = 0; t < n_tiles; ++t, ++tcount) {
-        // Threshold refresh: other items of the same queries (on any SM) lower tau_g while this item is
-        // streamed; once per tile the lanes rewrite the item's thresholds from the value they loaded one
-        // tile earlier (the filter may read the old or the new one: both are upper bounds).
-#ifndef NLSH_NO_REFRESH  // A/B: -DNLSH_NO_REFRESH
-        if (t > 0) {
-#else
-        if (false) {
-#endif
-#pragma unroll
-          for (int c = 0; c < kCh; ++c) {
-            if (32 * c + lane < rec.nq && tau_new[c] < tau_cur[c]) {
-              tau_cur[c] = tau_new[c];
-              s.thr_s[islot * NQ + 32 * c + lane] = make_thr<METRIC>(tau_new[c], cur.qn2[c], a.l2_slack);
-            }
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < kCh; ++c)
-          if (cur.qi[c] >= 0) tau_new[c] = __ldcg(a.tau_g + cur.qi[c]);
-        if (lane == 0) {
+        for (int t = 0; t < n_tiles; ++t, ++tcount) {
           const int trow0 = rec.row0 + t * kTile;
           {
             // The tile's row norms: a plain bulk copy needs a 16-byte aligned source, so it starts
             // at the 4-row boundary below the tile and stops at the last whole group of 4 rows of
             // the array (the filter reads the <= 3 rows after that directly).
             const unsigned mb = tcount % kMetaBufs;
-            MBAR_WAIT(&s.meta_empty[mb], ((tcount / kMetaBufs) & 1u) ^ 1u);
+            ROLE_WAIT(1, &s.meta_empty[mb], ((tcount / kMetaBufs) & 1u) ^ 1u);
             const long long m0 = trow0 & ~3ll;
-            long long avail = (a.n_rows & ~3ll) - m0;
+            long long avail = n_rows4 - m0;
             if (avail > kMetaFloats) avail = kMetaFloats;
             if (avail > 0) {
               mbar_arrive_expect_tx(&s.meta_full[mb], (unsigned)avail * 4u);
@@ -460,53 +547,52 @@ __global__ void __launch_bounds__(kThreads, 1)
           // next bucket and would be read for nothing (26 % of the traffic with 305-row buckets)
           const int rows_left = rec.row1 - trow0;
           const int sub = rows_left >= kTile ? 0 : (rows_left + 31) >> 5;
-          for (int kb = 0; kb < kblocks; ++kb, ++ring) {
-            const unsigned sl = ring % n_slots;
-            MBAR_WAIT(&s.empty_bar[sl], ((ring / n_slots) & 1u) ^ 1u);
+          const unsigned qbytes = WIDE ? kQBytes : 0u;
+          const unsigned tx = (sub == 0 ? kSlotBytes : (unsigned)sub * kSubBoxBytes) + qbytes;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            ROLE_WAIT(2, &s.empty_bar[sl], sl_par ^ 1u);
             unsigned char* dst = s.slots + (size_t)sl * kSlotStride;
             // a box is always written in full (rows / columns past the tensor are zero filled)
-            const unsigned qbytes = WIDE ? kQBytes : 0u;
+            mbar_arrive_expect_tx(&s.full_bar[sl], tx);
             if (sub == 0) {
-              mbar_arrive_expect_tx(&s.full_bar[sl], kSlotBytes + qbytes);
               tma_load_2d(dst, &map_x, kb * kTcBK, trow0, &s.full_bar[sl]);
             } else {
-              mbar_arrive_expect_tx(&s.full_bar[sl], (unsigned)sub * kSubBoxBytes + qbytes);
               for (int b = 0; b < sub; ++b)
                 tma_load_2d(dst + b * kSubBoxBytes, &map_x32, kb * kTcBK, trow0 + 32 * b, &s.full_bar[sl]);
             }
             if (WIDE) tma_load_2d(dst + kSlotBytes, &map_q, kb * kTcBK, rec.pair_base, &s.full_bar[sl]);
+            if (++sl == n_slots) {
+              sl = 0;
+              sl_par ^= 1u;
+            }
           }
         }
-        __syncwarp();
+        ++icount;
       }
-      __syncwarp();
-      ++icount;
-      cur = nx1;
-#pragma unroll
-      for (int c = 0; c < kCh; ++c) tau_cur[c] = tau_nx1[c];
-      nx1 = nx2;
-      nx2.rec = rec3;
+      ROLE_REPORT(21);  // wait itm_full, meta_empty, slot empty, -, total
     }
+    __syncwarp();
   } else if (warp == 1) {
     // =================================== MMA issuer =======================================
     if (lane == 0) {
+      ROLE_T0();
       const uint32_t idesc = make_tf32_idesc(NQ);
-      unsigned ring = 0, icount = 0, tcount = 0;
+      unsigned sl = 0, sl_par = 0;  // slot ring position and the parity of its current round
+      unsigned icount = 0, tcount = 0;
       while (true) {
         const int islot = (int)(icount % kItemBufs);
-        MBAR_WAIT(&s.q_full[islot], (icount / kItemBufs) & 1u);
+        ROLE_WAIT(0, &s.q_full[islot], (icount / kItemBufs) & 1u);
         const int nq = s.itm[islot].nq;
         if (nq == 0) break;
         const int n_tiles = (s.itm[islot].row1 - s.itm[islot].row0 + kTile - 1) / kTile;
         const unsigned char* qsrc = s.qbuf + (size_t)islot * kblocks * kQBytes;
         for (int t = 0; t < n_tiles; ++t, ++tcount) {
           const unsigned set = tcount % kSets;
-          MBAR_WAIT(&s.acc_empty[set], ((tcount / kSets) & 1u) ^ 1u);  // the filter drained this set
+          ROLE_WAIT(1, &s.acc_empty[set], ((tcount / kSets) & 1u) ^ 1u);  // the filter drained this set
           tc_fence_after();
           const uint32_t acc = tmem_base + set * (uint32_t)NQ;
-          for (int kb = 0; kb < kblocks; ++kb, ++ring) {
-            const unsigned sl = ring % n_slots;
-            MBAR_WAIT(&s.full_bar[sl], (ring / n_slots) & 1u);
+          for (int kb = 0; kb < kblocks; ++kb) {
+            ROLE_WAIT(2, &s.full_bar[sl], sl_par);
             tc_fence_after();
             const unsigned char* slot = s.slots + (size_t)sl * kSlotStride;
             const uint64_t da = make_kmajor_sw128_desc(slot);
@@ -516,11 +602,16 @@ __global__ void __launch_bounds__(kThreads, 1)
               tc_mma_tf32(acc, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc,
                           (kb > 0 || k8 > 0) ? 1u : 0u);
             tc_commit(&s.empty_bar[sl]);  // the slot may be refilled once these MMAs have read it
+            if (++sl == n_slots) {
+              sl = 0;
+              sl_par ^= 1u;
+            }
           }
           tc_commit(&s.acc_full[set]);
         }
         ++icount;
       }
+      ROLE_REPORT(11);  // wait q_full, acc_empty, slot full, -, total
     }
     __syncwarp();
   } else {
@@ -532,6 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int* q_row = s.wq_row + fw * kQueueCap;
     int* q_meta = s.wq_meta + fw * kQueueCap;
+    int* q_qi = s.wq_qi + fw * kQueueCap;
     ScoreCtx sc;
     sc.xs = a.xs;
     sc.ids = a.ids;
@@ -553,9 +645,37 @@ __global__ void __launch_bounds__(kThreads, 1)
     int count = 0;      // queued survivors (warp-uniform)
     unsigned n_surv = 0, n_batches = 0, n_flush = 0, n_appended = 0;
     unsigned icount = 0, tcount = 0;
+    // !QGLOBAL: queue entries refer to the item slot whose queries they need, so a slot is released only when
+    // the queue's front has passed the item's last entry - after the next full batch as a rule, and by
+    // scoring a partial batch only when the warp would otherwise wait (nothing is published to filter)
+    unsigned enq_total = 0, done_total = 0;  // entries queued / scored so far
+    unsigned wm[kItemBufs + 1];              // enq_total at the end of each filtered, unreleased item
+    int npend = 0;
+    unsigned rel = 0;                        // item count of the oldest unreleased item
+    auto release_ready = [&]() {
+      while (npend > 0 && (int)(done_total - wm[0]) >= 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.q_empty[rel % kItemBufs]);
+        ++rel;
+        --npend;
+#pragma unroll
+        for (int i = 0; i < kItemBufs; ++i) wm[i] = wm[i + 1];
+      }
+    };
+    ROLE_T0();
     while (true) {
       const int islot = (int)(icount % kItemBufs);
-      MBAR_WAIT(&s.q_full[islot], (icount / kItemBufs) & 1u);
+      if (!QGLOBAL && npend > 0 && !mbar_try_wait_short(&s.q_full[islot], (icount / kItemBufs) & 1u)) {
+        if (count > 0) {
+          score_batch<METRIC, QGLOBAL, V8>(sc, q_row, q_meta, q_qi, head, count, lane, n_appended);
+          head = (head + (unsigned)count) & (kQueueCap - 1);
+          done_total += (unsigned)count;
+          count = 0;
+          ++n_flush;
+        }
+        release_ready();
+      }
+      ROLE_WAIT(0, &s.q_full[islot], (icount / kItemBufs) & 1u);
       const TcItem rec = s.itm[islot];
       if (rec.nq == 0) break;
       const float* th = s.thr_s + islot * NQ;
@@ -566,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int row = rec.row0 + t * kTile + r_local;
         const bool valid = row < rec.row1;
         const unsigned mb = tcount % kMetaBufs;
-        MBAR_WAIT(&s.meta_full[mb], (tcount / kMetaBufs) & 1u);
+        ROLE_WAIT(1, &s.meta_full[mb], (tcount / kMetaBufs) & 1u);
         float xn = reinterpret_cast<const float*>(s.meta + (size_t)mb * kMetaBytes)[((rec.row0 + t * kTile) & 3) + r_local];
         if (row >= (a.n_rows & ~3ll)) xn = valid ? a.xnorm[row] : 0.f;
         __syncwarp();
@@ -580,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           rb = 0.f;
         }
         const unsigned set = tcount % kSets;
-        MBAR_WAIT(&s.acc_full[set], (tcount / kSets) & 1u);
+        ROLE_WAIT(2, &s.acc_full[set], (tcount / kSets) & 1u);
         tc_fence_after();
         unsigned masks[kCh];
 #pragma unroll
@@ -625,36 +745,43 @@ __global__ void __launch_bounds__(kThreads, 1)
               const unsigned e = (head + (unsigned)count + __popc(b & ((1u << lane) - 1u))) & (kQueueCap - 1);
               q_row[e] = row;
               q_meta[e] = QGLOBAL ? rec.pair_base + j : ((islot << 8) | j);
+              q_qi[e] = s.qi_s[islot * NQ + j];
             }
             const int added = __popc(b);
             count += added;
+            enq_total += (unsigned)added;
             n_surv += (unsigned)added;
             __syncwarp();
             if (count >= 32) {
-              score_batch<METRIC, QGLOBAL>(sc, q_row, q_meta, head, 32, lane, n_appended);
+              ROLE_TIC();
+              score_batch<METRIC, QGLOBAL, V8>(sc, q_row, q_meta, q_qi, head, 32, lane, n_appended);
+              ROLE_TOC(3);
               head = (head + 32u) & (kQueueCap - 1);
               count -= 32;
+              done_total += 32u;
               ++n_batches;
+              if (!QGLOBAL) release_ready();
             }
           }
         }
       }
-      // the item's queries leave shared memory with this arrive: score what is still queued
-      // (QGLOBAL entries do not refer to the item slot and stay queued across items)
-      if (!QGLOBAL && count > 0) {
-        score_batch<METRIC, QGLOBAL>(sc, q_row, q_meta, head, count, lane, n_appended);
-        head = (head + (unsigned)count) & (kQueueCap - 1);
-        count = 0;
-        ++n_flush;
+      if (QGLOBAL) {  // entries do not refer to the item slot and stay queued across items
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.q_empty[islot]);
+      } else {
+#pragma unroll
+        for (int i = 0; i <= kItemBufs; ++i)
+          if (i == npend) wm[i] = enq_total;
+        ++npend;
+        release_ready();
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.q_empty[islot]);
       ++icount;
     }
-    if (QGLOBAL && count > 0) {
-      score_batch<METRIC, QGLOBAL>(sc, q_row, q_meta, head, count, lane, n_appended);
+    if (count > 0) {
+      score_batch<METRIC, QGLOBAL, V8>(sc, q_row, q_meta, q_qi, head, count, lane, n_appended);
       ++n_flush;
     }
+    ROLE_REPORT(16);  // (sum over the 8 filter warps) wait q_full, meta_full, acc_full, full-batch scoring, total
     if (a.stats != nullptr) {
       // debug counters: [0] survivors of the filter, [1] full batches, [2] end-of-item batches,
       // [3] candidates appended (n_appended is per lane), [4] tiles this warp filtered
@@ -872,7 +999,7 @@ __global__ void __launch_bounds__(32 * kSeedWarps)
     for (int base = 32 * warp; base < n; base += 32 * kSeedWarps) {
       const int r = base + lane;
       float dist = 0.f;
-      if (r < n) dist = tc_thread_distance<METRIC, 8>(xs + (size_t)(r0 + r) * d_pad, qg, d);
+      if (r < n) dist = tc_thread_distance<METRIC, 8, false>(xs + (size_t)(r0 + r) * d_pad, qg, d);
       top.offer(dist, taken + r, r < n, k);
     }
     budget -= n;
@@ -987,10 +1114,10 @@ int nlsh_scan_tc_seed(const float* qn, long long n_queries, const int* probes, i
 }
 
 namespace {
-template <int METRIC, int NQ, bool WIDE, bool QGLOBAL>
+template <int METRIC, int NQ, bool WIDE, bool QGLOBAL, bool V8>
 int launch_variant(const TcScanArgs& a, const CUtensorMap& map_x, const CUtensorMap& map_x32,
                    const CUtensorMap& map_q, int grid, size_t smem, cudaStream_t st) {
-  auto kern = scan_tc_kernel<METRIC, NQ, WIDE, QGLOBAL>;
+  auto kern = scan_tc_kernel<METRIC, NQ, WIDE, QGLOBAL, V8>;
   NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kThreads, smem, st>>>(a, map_x, map_x32, map_q);
   return nlsh_check_cuda(nlsh_post_launch(), "scan_tc_kernel launch");
@@ -998,11 +1125,15 @@ int launch_variant(const TcScanArgs& a, const CUtensorMap& map_x, const CUtensor
 
 template <int METRIC>
 int launch_metric(const TcScanArgs& a, const CUtensorMap& map_x, const CUtensorMap& map_x32,
-                  const CUtensorMap& map_q, bool wide, bool qglobal, int grid, size_t smem, cudaStream_t st) {
-  if (a.nq_group == kTcNQMax) return launch_variant<METRIC, kTcNQMax, true, true>(a, map_x, map_x32, map_q, grid, smem, st);
-  if (wide) return launch_variant<METRIC, kTcNQ, true, true>(a, map_x, map_x32, map_q, grid, smem, st);
-  if (qglobal) return launch_variant<METRIC, kTcNQ, false, true>(a, map_x, map_x32, map_q, grid, smem, st);
-  return launch_variant<METRIC, kTcNQ, false, false>(a, map_x, map_x32, map_q, grid, smem, st);
+                  const CUtensorMap& map_q, bool wide, bool qglobal, bool v8, int grid, size_t smem, cudaStream_t st) {
+#define NLSH_TC_LAUNCH(NQ, WIDE, QGLOBAL)                                                                  \
+  return v8 ? launch_variant<METRIC, NQ, WIDE, QGLOBAL, true>(a, map_x, map_x32, map_q, grid, smem, st)    \
+            : launch_variant<METRIC, NQ, WIDE, QGLOBAL, false>(a, map_x, map_x32, map_q, grid, smem, st)
+  if (a.nq_group == kTcNQMax) { NLSH_TC_LAUNCH(kTcNQMax, true, true); }
+  if (wide) { NLSH_TC_LAUNCH(kTcNQ, true, true); }
+  if (qglobal) { NLSH_TC_LAUNCH(kTcNQ, false, true); }
+  NLSH_TC_LAUNCH(kTcNQ, false, false);
+#undef NLSH_TC_LAUNCH
 }
 }  // namespace
 
@@ -1012,17 +1143,26 @@ int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {
   if (a.nq_group != kTcNQMax) a.nq_group = kTcNQ;
   // wide rows, or 128 queries per item: the queries' K blocks travel with the row tiles
   const bool wide = a.kblocks > kMaxKBlocks || a.nq_group == kTcNQMax;
-  // Scorer query source: the pair-ordered global copy (QGLOBAL), which spares the partial batch every warp
-  // would score at the end of every item (measured: config 4 0.943 against 0.957 ms, 8-GPU shard 0.191 against
-  // 0.205 ms); NLSH_TC_QGLOBAL=0 selects the item's shared-memory copy instead (A/B runs).
-  bool qglobal = true;
+  // Scorer query source.  The item's shared-memory copy halves the scorer's L2 requests (a survivor then costs
+  // its 512-byte row alone) but ties queue entries to item slots: fine when an item yields a batch or more per
+  // warp (buckets of >= 8 tiles), while on 8-GPU shards (2 - 3 tiles per bucket) warps would sit on several
+  // unreleased items, so short items take the pair-ordered global copy (QGLOBAL) - as wide rows must.
+  // NLSH_TC_QGLOBAL=0/1 overrides (A/B runs).
+  bool qglobal = wide || a.avg_item_rows < 8 * kTile;
   if (const char* env = getenv("NLSH_TC_QGLOBAL")) qglobal = wide || atoi(env) != 0;
   int n_slots = kMaxSlots;
-  // each K block's slot is freed by its own tcgen05.commit, so any ring depth >= 2 makes progress
-  while (n_slots > 3 && scan_tc_smem(a.kblocks, n_slots, wide, a.nq_group) > 224 * 1024) --n_slots;
+  // each K block's slot is freed by its own tcgen05.commit, so any ring depth >= 2 makes progress.  With the
+  // queries read from global memory the scorer lives on L1 hits, and shared memory above 196 KB leaves L1 only
+  // 28 KB: those variants stop at the 196 KB carve-out (measured: config 3 0.33 -> 0.23 ms, shard 0.213 -> 0.184).
+  size_t smem_limit = (qglobal ? 195 : 224) * 1024;  // a block's share of a carve-out is 1 KB less
+  if (const char* env = getenv("NLSH_TC_SMEM_KB")) {  // A/B runs: up to the 227 KB a block may opt in to
+    const int v = atoi(env);
+    if (v >= 64 && v <= 227) smem_limit = (size_t)v * 1024;
+  }
+  while (n_slots > 3 && scan_tc_smem(a.kblocks, n_slots, wide, a.nq_group) > smem_limit) --n_slots;
   if (const char* env = getenv("NLSH_TC_SLOTS")) {  // A/B runs
     const int v = atoi(env);
-    if (v >= 3 && v < n_slots) n_slots = v;
+    if (v >= 3 && v <= kMaxSlots && scan_tc_smem(a.kblocks, v, wide, a.nq_group) <= 227 * 1024) n_slots = v;
   }
   a.n_slots = n_slots;
   const size_t smem = scan_tc_smem(a.kblocks, n_slots, wide, a.nq_group);
@@ -1037,7 +1177,11 @@ int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {
   if (const char* env = getenv("NLSH_TC_GRID")) grid = atoi(env);
   if (grid < 1) grid = 1;
   if (grid > nlsh_num_sms()) grid = nlsh_num_sms();
+  // 32-byte loads in the scorer when every row of xs and qs starts on a 32-byte boundary (NLSH_TC_V8=0: A/B runs)
+  bool v8 = a.d_pad % 8 == 0 && (reinterpret_cast<uintptr_t>(a.xs) & 31) == 0 &&
+            (reinterpret_cast<uintptr_t>(a.qs) & 31) == 0;
+  if (const char* env = getenv("NLSH_TC_V8")) v8 = v8 && atoi(env) != 0;
   if (metric == NLSH_METRIC_L2)
-    return launch_metric<NLSH_METRIC_L2>(a, map_x, map_x32, map_q, wide, qglobal, grid, smem, st);
-  return launch_metric<NLSH_METRIC_ANGULAR>(a, map_x, map_x32, map_q, wide, qglobal, grid, smem, st);
+    return launch_metric<NLSH_METRIC_L2>(a, map_x, map_x32, map_q, wide, qglobal, v8, grid, smem, st);
+  return launch_metric<NLSH_METRIC_ANGULAR>(a, map_x, map_x32, map_q, wide, qglobal, v8, grid, smem, st);
 }

@@ -76,36 +76,67 @@ int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st);
 // difference form sum((q - x + 1e-6)^2) (nlsh/data.py:201, the root is taken in the merge), ANGULAR
 // 1 - <q, x> / max(|x|, 1e-8) for a pre-normalised q (nlsh/data.py:109).
 // QLoad::load4(v) returns the query's columns 4 v .. 4 v + 3, QLoad::load1(c) column c.
-template <int METRIC, int kBatch, typename QLoad>
+// 32 bytes per load instruction (sm_100: LDG.256): a lane's 16-byte loads of one row are 32 different cache
+// lines per warp instruction, so the scorer is bound by L1 wavefronts, and the wide load halves them.
+// p must be 32-byte aligned.
+__device__ __forceinline__ void tc_ldg256(const float* p, float4& a, float4& b) {
+  // not volatile: a pure load the compiler may hoist and batch like __ldg; the rows are read once, so they are
+  // kept out of L1 (what L1 there is beside the kernel's shared memory serves the query vectors)
+  asm("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+
+__device__ __forceinline__ void tc_ldg256_keep(const float* p, float4& a, float4& b) {
+  asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p));
+}
+
+// V8: the row (and a global query) is read 32 bytes at a time; needs d_pad % 8 == 0 and 32-byte aligned bases.
+template <int METRIC, int kBatch, bool V8, typename QLoad>
 __device__ __forceinline__ float tc_thread_distance(const float* __restrict__ xrow, const QLoad& q, int d) {
+  static_assert(kBatch % 2 == 0, "kBatch counts float4 loads, two per 32-byte load");
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
   const int nv = d >> 2, tail = d & 3;
   // kBatch row loads (16 bytes each) are in flight per step
   for (int v0 = 0; v0 < nv; v0 += kBatch) {
-    float4 xv[kBatch];
+    float4 xv[kBatch], qv[kBatch];
+    if (V8) {
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i)
-      xv[i] = (v0 + i < nv) ? __ldg(reinterpret_cast<const float4*>(xrow) + v0 + i)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < kBatch; i += 2) {
+        if (v0 + i < nv) {  // the pair's second half may be the partial float4 (inside the padded row)
+          tc_ldg256(xrow + 4 * (v0 + i), xv[i], xv[i + 1]);
+        } else {
+          xv[i] = xv[i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i)
+        xv[i] = (v0 + i < nv) ? __ldg(reinterpret_cast<const float4*>(xrow) + v0 + i)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
       if (v0 + i < nv) {
-        const float4 qv = q.load4(v0 + i);
+        if (!V8) qv[i] = q.load4(v0 + i);
+        else if ((i & 1) == 0) q.load8(v0 + i, qv[i], qv[i + 1]);  // the compiler hoists these as registers allow
         if (METRIC == NLSH_METRIC_L2) {
-          const float t0 = __fadd_rn(__fsub_rn(qv.x, xv[i].x), 1e-6f);
-          const float t1 = __fadd_rn(__fsub_rn(qv.y, xv[i].y), 1e-6f);
-          const float t2 = __fadd_rn(__fsub_rn(qv.z, xv[i].z), 1e-6f);
-          const float t3 = __fadd_rn(__fsub_rn(qv.w, xv[i].w), 1e-6f);
+          const float t0 = __fadd_rn(__fsub_rn(qv[i].x, xv[i].x), 1e-6f);
+          const float t1 = __fadd_rn(__fsub_rn(qv[i].y, xv[i].y), 1e-6f);
+          const float t2 = __fadd_rn(__fsub_rn(qv[i].z, xv[i].z), 1e-6f);
+          const float t3 = __fadd_rn(__fsub_rn(qv[i].w, xv[i].w), 1e-6f);
           s0 = fmaf(t0, t0, s0);
           s1 = fmaf(t1, t1, s1);
           s2 = fmaf(t2, t2, s2);
           s3 = fmaf(t3, t3, s3);
         } else {
-          s0 = fmaf(qv.x, xv[i].x, s0);
-          s1 = fmaf(qv.y, xv[i].y, s1);
-          s2 = fmaf(qv.z, xv[i].z, s2);
-          s3 = fmaf(qv.w, xv[i].w, s3);
+          s0 = fmaf(qv[i].x, xv[i].x, s0);
+          s1 = fmaf(qv[i].y, xv[i].y, s1);
+          s2 = fmaf(qv[i].z, xv[i].z, s2);
+          s3 = fmaf(qv[i].w, xv[i].w, s3);
           x0 = fmaf(xv[i].x, xv[i].x, x0);
           x1 = fmaf(xv[i].y, xv[i].y, x1);
           x2 = fmaf(xv[i].z, xv[i].z, x2);
@@ -135,6 +166,7 @@ __device__ __forceinline__ float tc_thread_distance(const float* __restrict__ xr
 struct TcQueryGlobal {
   const float* q;
   __device__ __forceinline__ float4 load4(int v) const { return __ldg(reinterpret_cast<const float4*>(q) + v); }
+  __device__ __forceinline__ void load8(int v, float4& a, float4& b) const { tc_ldg256_keep(q + 4 * v, a, b); }
   __device__ __forceinline__ float load1(int c) const { return __ldg(q + c); }
 };
 #endif

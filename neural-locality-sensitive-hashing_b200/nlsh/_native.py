@@ -58,6 +58,7 @@ PROTOTYPES = {
     "nlsh_mlp_hash_f32": (ctypes.c_int, [_vp, _i64, _i32, _LP, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "nlsh_codes_from_logits": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "nlsh_topp_probes": (ctypes.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "nlsh_sample_probes": (ctypes.c_int, [_vp, _i64, _i32, _i32, _i32, ctypes.c_uint64, _vp, _vp]),
     "nlsh_build_workspace_bytes": (_sz, [_i64, _i32]),
     "nlsh_build_csr": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nlsh_query_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i64, _i64]),
@@ -285,6 +286,18 @@ def topp_probes(logits, head, p):
     with torch.cuda.device(logits.device):
         rc = lib().nlsh_topp_probes(_ptr(logits), n, hs, head, p, _ptr(probes), _stream())
     _check(rc, "nlsh_topp_probes")
+    return probes
+
+
+def sample_probes(logits, head, p, seed):
+    """Bernoulli-sampled probe codes int32 [n, p] (column 0 = hard code), hashings.py:77-81."""
+    logits = _f32c(logits, "logits")
+    n, hs = logits.shape
+    probes = torch.empty((n, p), dtype=torch.int32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        rc = lib().nlsh_sample_probes(_ptr(logits), n, hs, head, p, int(seed) & (2 ** 64 - 1), _ptr(probes),
+                                      _stream())
+    _check(rc, "nlsh_sample_probes")
     return probes
 
 

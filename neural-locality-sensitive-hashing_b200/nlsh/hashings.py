@@ -223,26 +223,33 @@ class MultivariateBernoulli:
     def layer_specs(self):
         return extract_layers(self._hasher._encoder, self._hasher.output_layer)
 
-    def hash_tensors(self, query_vectors, n=1, want_logits=False, workspace=None):
+    def hash_tensors(self, query_vectors, n=1, want_logits=False, workspace=None, sample_seed=None):
         """-> (codes int32 [B], probes int32 [B, n] | None, logits fp32 [B, hs] | None).
 
         codes[i] is the hard code (`probs > 0.5`, hashings.py:72); probes[i, 0] == codes[i]
-        and probes[i, 1:] are the next most probable codes (-1 padded)."""
+        and probes[i, 1:] are the next most probable codes (-1 padded) - or, with `sample_seed`
+        (an int), n - 1 draws of Bernoulli(probs) as in hashings.py:77-81 (rows may then repeat a
+        code; the reference collects them into a set), reproducible for a given seed."""
         if n < 1:
             raise ValueError(f"`n` should be positive integer, but got {n}")
         need_logits = want_logits or n > 1
         logits, codes = _native.mlp_hash(query_vectors, self.layer_specs(), self.head,
                                          want_logits=need_logits, want_codes=True, workspace=workspace)
-        probes = _native.topp_probes(logits, self.head, n) if n > 1 else None
+        if n == 1:
+            probes = None
+        elif sample_seed is None:
+            probes = _native.topp_probes(logits, self.head, n)
+        else:
+            probes = _native.sample_probes(logits, self.head, n, sample_seed)
         return codes, probes, (logits if want_logits else None)
 
-    def hash(self, query_vectors, n=1) -> List[Set[int]]:
+    def hash(self, query_vectors, n=1, sample_seed=None) -> List[Set[int]]:
         # hashings.py:66-92
         if n < 1:
             raise ValueError(f"`n` should be positive integer, but got {n}")
         if query_vectors.shape[0] == 0:
             return []
-        codes, probes, _ = self.hash_tensors(query_vectors, n)
+        codes, probes, _ = self.hash_tensors(query_vectors, n, sample_seed=sample_seed)
         if probes is None:
             return [{c} for c in codes.cpu().tolist()]
         return codes_to_sets(probes)

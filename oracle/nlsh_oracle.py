@@ -146,6 +146,47 @@ def topp_probes(logits, head: int, p: int) -> np.ndarray:
     return out
 
 
+def _philox4x32_10(ctr, key):
+    """Philox-4x32-10 (Salmon et al., SC'11) on uint32 numpy arrays: ctr [4, ...], key [2, ...]."""
+    c = [np.asarray(v, dtype=np.uint64) for v in ctr]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k0) & m32, p1 & m32, ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & m32, p0 & m32]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
+    return c
+
+
+def sample_probes(logits, head: int, p: int, seed: int):
+    """hashings.py:66-81 with n = p: column 0 the hard code, columns 1.. the packed codes of p - 1 draws of
+    torch.distributions.Bernoulli(probs) - restated with the counter-based generator of this repo's kernel
+    (uniform u(row, j, bit) = (Philox(seed; row, j, bit // 4)[bit % 4] >> 8) * 2^-24, bit set iff u < prob), since
+    torch's own sampling stream depends on torch's launch geometry and cannot be reproduced.  Returns (probes
+    int32 [n, p], margin fp32 [n, p]: min over bits of |u - prob|, so a test can skip draws that a one-ulp
+    difference in exp / tanh could flip)."""
+    l = torch.as_tensor(np.asarray(logits, dtype=np.float32))
+    n, hs = l.shape
+    probs = (torch.tanh(l) / 2. + 0.5 if head == HEAD_TANH else torch.sigmoid(l)).numpy().astype(np.float32)
+    rows = np.arange(n, dtype=np.uint64)[:, None, None]
+    js = np.arange(p, dtype=np.uint64)[None, :, None]
+    groups = np.arange((hs + 3) // 4, dtype=np.uint64)[None, None, :]
+    shape = (n, p, (hs + 3) // 4)
+    words = _philox4x32_10([np.broadcast_to(rows & np.uint64(0xFFFFFFFF), shape), np.broadcast_to(rows >> np.uint64(32), shape),
+                            np.broadcast_to(js, shape), np.broadcast_to(groups, shape)],
+                           (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    u = np.stack(words, axis=-1).reshape(n, p, -1)[:, :, :hs]            # [n, p, hs] uint64 words
+    u = ((u >> np.uint64(8)).astype(np.float32) * np.float32(2.0 ** -24))
+    bits = (u < probs[:, None, :])
+    bits[:, 0, :] = hard_bits(l, head).numpy()
+    margin = np.abs(u - probs[:, None, :]).min(axis=2)
+    margin[:, 0] = 1.0
+    weights = (1 << np.arange(hs - 1, -1, -1)).astype(np.int64)
+    return (bits.astype(np.int64) * weights).sum(axis=2).astype(np.int32), margin
+
+
 # ---------------------------------------------------------------------------------------
 # nlsh/indexer.py
 # ---------------------------------------------------------------------------------------

@@ -1,0 +1,16 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+T=${TAG:-r2e}
+( timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/${T}_tests.log 2>&1; echo "exit $?" >> gpurun_out/${T}_tests.log
+( timeout 300 python scripts/dbg_tc_roles.py cfg4_10m_x128_4096b 8 1250000 ) > gpurun_out/${T}_roles_shard.json 2> gpurun_out/${T}_roles_shard.err
+( timeout 300 python scripts/dbg_tc_roles.py cfg4_10m_x128_4096b 8 ) > gpurun_out/${T}_roles_full.json 2> gpurun_out/${T}_roles_full.err
+V=${VARS:-"NLSH_TC_QGLOBAL=0;NLSH_TC_QGLOBAL=1;NLSH_TC_QGLOBAL=1,NLSH_TC_SMEM_KB=224;NLSH_TC_V8=0"}
+( TC_VARIANTS="$V" timeout 300 python scripts/dbg_tc_variants.py cfg4_10m_x128_4096b 8 1250000 ) > gpurun_out/${T}_variants_shard.jsonl 2> gpurun_out/${T}_variants_shard.err
+( TC_VARIANTS="$V" timeout 300 python scripts/dbg_tc_variants.py cfg4_10m_x128_4096b 8 ) > gpurun_out/${T}_variants_full.jsonl 2> gpurun_out/${T}_variants_full.err
+( NLSH_B200_LIB=$PWD/neural-locality-sensitive-hashing_b200/lib/libnlsh_b200_qs16.so TC_VARIANTS="NLSH_TC_QGLOBAL=0" timeout 300 python scripts/dbg_tc_variants.py cfg4_10m_x128_4096b 8 ) > gpurun_out/${T}_variants_full_qs16.jsonl 2> gpurun_out/${T}_variants_full_qs16.err
+( TC_VARIANTS="$V" timeout 300 python scripts/dbg_tc_variants.py cfg1_100k_x128_16b 2 ) > gpurun_out/${T}_variants_cfg1.jsonl 2> gpurun_out/${T}_variants_cfg1.err
+( TC_VARIANTS="$V" timeout 300 python scripts/dbg_tc_variants.py cfg2_1m_x128_256b 4 ) > gpurun_out/${T}_variants_cfg2.jsonl 2> gpurun_out/${T}_variants_cfg2.err
+( TC_VARIANTS="$V" timeout 300 python scripts/dbg_tc_variants.py cfg3_1.2m_x100_1024b_angular 2 ) > gpurun_out/${T}_variants_cfg3.jsonl 2> gpurun_out/${T}_variants_cfg3.err
+( TC_VARIANTS="NLSH_TC_SMEM_KB=224;NLSH_TC_V8=0" timeout 300 python scripts/dbg_tc_variants.py cfg5_1m_x960_512b_k100 128 ) > gpurun_out/${T}_variants_cfg5.jsonl 2> gpurun_out/${T}_variants_cfg5.err
+tail -n 3 gpurun_out/${T}_tests.log; cat gpurun_out/${T}_roles_shard.json gpurun_out/${T}_roles_full.json | cut -c1-1300; for f in shard full full_qs16 cfg1 cfg2 cfg3 cfg5; do echo "== $f"; cut -c1-300 gpurun_out/${T}_variants_$f.jsonl; tail -n 2 gpurun_out/${T}_variants_$f.err; done

@@ -77,6 +77,55 @@ def test_topp_probes_match_specification(oracle, hs, p):
         assert np.array_equal(got[:, 0], _native.codes_from_logits(l.cuda(), head).cpu().numpy())
 
 
+@pytest.mark.parametrize("hs,p", [(4, 2), (7, 9), (12, 16), (15, 33)])
+def test_sampled_probes_match_the_restated_bernoulli_draws(oracle, hs, p):
+    """hashings.py:77-81: hard code + n - 1 Bernoulli(probs) draws.  The kernel's draws equal the oracle's
+    (same Philox counters) except where a uniform sits within 1e-6 of the probability; the hard-code column is
+    bit-exact; a different seed gives different draws; the flip frequency follows sigmoid(logit)."""
+    from nlsh import _native
+    l = torch.randn(300, hs, generator=torch.Generator().manual_seed(hs * 7 + p)) * 1.5
+    for head in (_native.HEAD_SIGMOID, _native.HEAD_TANH):
+        got = _native.sample_probes(l.cuda(), head, p, 1234).cpu().numpy()
+        want, margin = oracle.sample_probes(l.numpy(), head, p, 1234)
+        safe = margin > 1e-6
+        assert safe.mean() > 0.99
+        assert np.array_equal(got[safe], want[safe])
+        assert np.array_equal(got[:, 0], _native.codes_from_logits(l.cuda(), head).cpu().numpy())
+        assert np.array_equal(got, _native.sample_probes(l.cuda(), head, p, 1234).cpu().numpy())
+        assert not np.array_equal(got[:, 1:], _native.sample_probes(l.cuda(), head, p, 99).cpu().numpy()[:, 1:])
+    # distribution: one row of logits repeated, many draws -> per-bit frequency ~ sigmoid(logit)
+    row = torch.tensor([[-2.0, -0.5, 0.0, 0.7, 3.0]])
+    draws = _native.sample_probes(row.repeat(4000, 1).cuda(), _native.HEAD_SIGMOID, 9, 7).cpu().numpy()[:, 1:]
+    bits = (draws[..., None] >> np.arange(4, -1, -1)) & 1
+    freq = bits.reshape(-1, 5).mean(axis=0)
+    assert np.abs(freq - torch.sigmoid(row[0]).numpy()).max() < 0.01, freq
+
+
+def test_sampled_hash_sets_feed_the_index(oracle):
+    """MultivariateBernoulli.hash(x, n, sample_seed=...) returns the reference's List[Set[int]] (every set
+    holds the hard code, at most n codes) and Indexer.query accepts sampled probe rows with repeats."""
+    import torch.nn.functional as F
+    from encoders import MultiLayerRelu
+    from nlsh.hashings import MultivariateBernoulli
+    from nlsh.indexer import Indexer
+    torch.manual_seed(3)
+    h = MultivariateBernoulli(MultiLayerRelu(32, [64]), 6, F.pairwise_distance)
+    h.train_mode(False)
+    X = torch.randn(5000, 32, generator=torch.Generator().manual_seed(1)).cuda()
+    Q = torch.randn(40, 32, generator=torch.Generator().manual_seed(2)).cuda()
+    sets = h.hash(Q, n=5, sample_seed=11)
+    hard = h.hash(Q, n=1)
+    assert all(len(s) <= 5 and next(iter(b)) in s for s, b in zip(sets, hard))
+    idx = Indexer(h, X, F.pairwise_distance)
+    _, probes, _ = h.hash_tensors(Q, 5, sample_seed=11)
+    ids, dists, ncand = idx.query_tensors(Q, k=5, probes=probes)
+    index2row = oracle.build_index([{int(c)} for c in h.hash_tensors(X, 1)[0].cpu().tolist()])
+    o_ids, o_d, o_n = oracle.query(X.cpu(), index2row, Q.cpu(), sets, "l2", 5)
+    assert ncand.cpu().tolist() == o_n
+    for q in range(40):
+        np.testing.assert_allclose(dists[q, :len(o_d[q])].cpu().numpy(), o_d[q], rtol=1e-5)
+
+
 @pytest.mark.parametrize("n,d,hidden,hs", [(1, 128, [256, 256], 12), (4097, 100, [256, 256], 10),
                                            (70001, 128, [256, 256], 8), (3000, 960, [256, 256], 9),
                                            (513, 30, [17], 3), (1000, 128, [64, 64], 12)])

@@ -157,3 +157,15 @@ def test_oracle_nearest_exclude_positive_small_case(oracle):
     got = oracle.nearest_exclude_positive(v, "l2sq", pos).tolist()
     # row 0: not itself, not 1 -> 2;  row 1: not 0 -> 2;  row 2: not 1 -> 3;  row 3: not 2 -> 1;  row 4: not 3 -> 2
     assert got == [2, 2, 3, 1, 2]
+
+
+def test_philox_known_answers():
+    """The oracle's Philox-4x32-10 (sample_probes) against the published Random123 known-answer vectors."""
+    from oracle import nlsh_oracle as oracle
+    z = [np.zeros(1)] * 4
+    assert [int(w[0]) for w in oracle._philox4x32_10(z, (0, 0))] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = [np.full(1, 0xffffffff)] * 4
+    assert [int(w[0]) for w in oracle._philox4x32_10(f, (0xffffffff, 0xffffffff))] == \
+        [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    probes, margin = oracle.sample_probes(np.zeros((4, 5), dtype=np.float32), oracle.HEAD_SIGMOID, 6, 1)
+    assert probes.shape == (4, 6) and (probes[:, 0] == 0).all() and (margin[:, 0] == 1).all()
