@@ -115,7 +115,11 @@ constexpr int kMaxSlots = 16;
 constexpr int kMetaFloats = kTile + 4;          // a tile's row norms, from the 16-byte boundary below its first row
 constexpr uint32_t kMetaBytes = 528;            // kMetaFloats * 4 (a multiple of 16: bulk-copy destination)
 constexpr int kMetaBufs = 16;                   // row-norm ring depth (tiles)
-constexpr int kItemBufs = 4;                    // item ring depth: buckets of a few tiles are shorter than the
+#ifndef NLSH_TC_STATE_DEEP  // A/B builds: make variant NAME=sb4 DEFS=-DNLSH_TC_STATE_DEEP=4
+#define NLSH_TC_STATE_DEEP 4
+#endif
+constexpr int kStateBufsDeep = NLSH_TC_STATE_DEEP;              // item-state ring depth when the scorer does not use the item's queries
+constexpr int kItemBufs = 4;                    // query-buffer ring depth: buckets of a few tiles are shorter than the
                                                 // pipeline, so several items must be in flight
 constexpr int kMaxKBlocks = 4;                  // d_pad <= 128: the item's queries stay in shared memory
 constexpr int kMaxWideKBlocks = 128;            // WIDE: d_pad <= 4096
@@ -164,19 +168,21 @@ struct SmemLayout {
   unsigned char* slots;   // [n_slots][16 KB (+ NQ * 128 bytes of queries, WIDE)]
   unsigned char* qbuf;    // [kItemBufs][kblocks][NQ * 128 bytes] (not WIDE)
   unsigned char* meta;    // [kMetaBufs][kMetaBytes] row norms
-  float* thr_s;           // [kItemBufs][NQ] filter thresholds
-  float* tau_s;           // [kItemBufs][NQ] the bound each threshold was made from (planner only)
-  float* qn2_s;           // [kItemBufs][NQ] |q|^2 (planner only)
-  int* qi_s;              // [kItemBufs][NQ] query indices (-1 unused)
-  TcItem* itm;            // [kItemBufs]
+  // item state ring, [n_state] entries (state_bufs(nq)); the item's query buffer is ring slot icount % kItemBufs
+  float* thr_s;           // [n_state][NQ] filter thresholds
+  float* tau_s;           // [n_state][NQ] the bound each threshold was made from (planner only)
+  float* qn2_s;           // [n_state][NQ] |q|^2 (planner only)
+  int* qi_s;              // [n_state][NQ] query indices (-1 unused)
+  TcItem* itm;            // [n_state]
   int* wq_row;            // [kFilterWarps][kQueueCap] survivor queues: row of x_sorted
   int* wq_meta;           // [kFilterWarps][kQueueCap] pair index (QGLOBAL) or (item slot << 8) | query j
   int* wq_qi;             // [kFilterWarps][kQueueCap] query index
   uint64_t* full_bar;     // [kMaxSlots]
   uint64_t* empty_bar;    // [kMaxSlots]
-  uint64_t* q_full;       // [kItemBufs] item state + queries in shared memory
-  uint64_t* q_empty;      // [kItemBufs]
-  uint64_t* itm_full;     // [kItemBufs] item state alone (what the tile streamer needs)
+  uint64_t* itm_full;     // [kStateBufsDeep] item state published
+  uint64_t* q_empty;      // [kStateBufsDeep] item state released by every filter warp
+  uint64_t* qb_full;      // [kItemBufs] the item's queries have landed in their buffer (not WIDE)
+  uint64_t* qb_empty;     // [kItemBufs] the item's MMAs have read them
   uint64_t* acc_full;     // [kMaxAccSets]
   uint64_t* acc_empty;    // [kMaxAccSets]
   uint64_t* meta_full;    // [kMetaBufs]
@@ -184,11 +190,14 @@ struct SmemLayout {
   uint32_t* tmem_slot;
 };
 
+// Depth of the item-state ring in shared memory (sized for the deepest user of a group size).
+__host__ __device__ constexpr int state_bufs(int nq) { return nq == kTcNQ ? kStateBufsDeep : kItemBufs; }
+
 __host__ __device__ inline size_t smem_fixed_bytes(int kblocks, bool wide, int nq) {
   return (wide ? 0 : (size_t)kItemBufs * kblocks * nq * 128) + (size_t)kMetaBufs * kMetaBytes +
-         4 * kItemBufs * nq * sizeof(float) + kItemBufs * sizeof(TcItem) +
+         4 * state_bufs(nq) * nq * sizeof(float) + state_bufs(nq) * sizeof(TcItem) +
          3 * kFilterWarps * kQueueCap * sizeof(int) +
-         (2 * kMaxSlots + 3 * kItemBufs + 2 * kMaxAccSets + 2 * kMetaBufs) * sizeof(uint64_t) + 16;
+         (2 * kMaxSlots + 2 * kStateBufsDeep + 2 * kItemBufs + 2 * kMaxAccSets + 2 * kMetaBufs) * sizeof(uint64_t) + 16;
 }
 
 __device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int n_slots, int kblocks, bool wide, int nq) {
@@ -197,19 +206,21 @@ __device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int n_slot
   s.qbuf = s.slots + (size_t)n_slots * (kSlotBytes + (wide ? nq * 128u : 0u));
   s.meta = s.qbuf + (wide ? 0 : (size_t)kItemBufs * kblocks * nq * 128);
   s.thr_s = reinterpret_cast<float*>(s.meta + (size_t)kMetaBufs * kMetaBytes);
-  s.tau_s = s.thr_s + kItemBufs * nq;
-  s.qn2_s = s.tau_s + kItemBufs * nq;
-  s.qi_s = reinterpret_cast<int*>(s.qn2_s + kItemBufs * nq);
-  s.itm = reinterpret_cast<TcItem*>(s.qi_s + kItemBufs * nq);
-  s.wq_row = reinterpret_cast<int*>(s.itm + kItemBufs);
+  const int ns = state_bufs(nq);
+  s.tau_s = s.thr_s + ns * nq;
+  s.qn2_s = s.tau_s + ns * nq;
+  s.qi_s = reinterpret_cast<int*>(s.qn2_s + ns * nq);
+  s.itm = reinterpret_cast<TcItem*>(s.qi_s + ns * nq);
+  s.wq_row = reinterpret_cast<int*>(s.itm + ns);
   s.wq_meta = s.wq_row + kFilterWarps * kQueueCap;
   s.wq_qi = s.wq_meta + kFilterWarps * kQueueCap;
   s.full_bar = reinterpret_cast<uint64_t*>(s.wq_qi + kFilterWarps * kQueueCap);
   s.empty_bar = s.full_bar + kMaxSlots;
-  s.q_full = s.empty_bar + kMaxSlots;
-  s.q_empty = s.q_full + kItemBufs;
-  s.itm_full = s.q_empty + kItemBufs;
-  s.acc_full = s.itm_full + kItemBufs;
+  s.itm_full = s.empty_bar + kMaxSlots;
+  s.q_empty = s.itm_full + kStateBufsDeep;
+  s.qb_full = s.q_empty + kStateBufsDeep;
+  s.qb_empty = s.qb_full + kItemBufs;
+  s.acc_full = s.qb_empty + kItemBufs;
   s.acc_empty = s.acc_full + kMaxAccSets;
   s.meta_full = s.acc_empty + kMaxAccSets;
   s.meta_empty = s.meta_full + kMetaBufs;
@@ -334,6 +345,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr int kSets = kTmemCols / NQ;         // TMEM accumulator ring depth
   static_assert(kSets % kGroups == 0 && kSets >= 2 && kSets <= kMaxAccSets, "accumulator ring");
   constexpr uint32_t kQBytes = NQ * 128u;       // one K block of the item's queries
+  // Item-state ring depth.  With the scorer's queries in global memory an item's query buffer is dead once its
+  // MMAs have run, so the state ring (thresholds, query indices: 0.5 KB per item) runs 16 items deep while
+  // the 16 KB query buffers recycle behind the MMA issuer - on 8-GPU shards (2 - 3 tiles per item) four items
+  // were not enough to keep tiles in flight while a filter warp scores a batch.  Scorer queries in shared
+  // memory: a queue entry pins its item's buffer, one ring, four deep.
+  constexpr int kSB = (QGLOBAL && NQ == kTcNQ) ? kStateBufsDeep : kItemBufs;
   extern __shared__ unsigned char stc_smem_raw[];
   unsigned char* base = stc_smem_raw + ((1024u - (smem_u32(stc_smem_raw) & 1023u)) & 1023u);
   const SmemLayout s = carve_smem(base, a.n_slots, a.kblocks, WIDE, NQ);
@@ -344,6 +361,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int lane = tid & 31;
   const unsigned n_slots = (unsigned)a.n_slots;
   const int kblocks = a.kblocks;
+  // accumulator sets in use (a power of two <= kSets): how many tiles the MMAs may run ahead of the filter
+  const unsigned sets_log2 = (unsigned)a.sets_log2 < (unsigned)(31 - __clz(kSets)) ? (unsigned)a.sets_log2 : (unsigned)(31 - __clz(kSets));
+  const unsigned sets_mask = (1u << sets_log2) - 1u;
 
   if (tid == 0) {
     for (int i = 0; i < a.n_slots; ++i) {
@@ -354,10 +374,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&s.meta_full[i], 1);
       mbar_init(&s.meta_empty[i], 4);
     }
-    for (int i = 0; i < kItemBufs; ++i) {
-      mbar_init(&s.q_full[i], 1);
-      mbar_init(&s.q_empty[i], kFilterWarps);
+    for (int i = 0; i < kStateBufsDeep; ++i) {
       mbar_init(&s.itm_full[i], 1);
+      mbar_init(&s.q_empty[i], kFilterWarps);
+    }
+    for (int i = 0; i < kItemBufs; ++i) {
+      mbar_init(&s.qb_full[i], 1);
+      mbar_init(&s.qb_empty[i], 1);
     }
     for (int i = 0; i < kSets; ++i) {
       mbar_init(&s.acc_full[i], 1);
@@ -415,9 +438,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     // new value: both are upper bounds; the planner is the only writer of the item slots).
     auto refresh = [&](int n_live) {
 #ifndef NLSH_NO_REFRESH  // A/B: -DNLSH_NO_REFRESH
-      float t[kItemBufs][kCh];
+      float t[kSB][kCh];
 #pragma unroll
-      for (int b = 0; b < kItemBufs; ++b) {
+      for (int b = 0; b < kSB; ++b) {
 #pragma unroll
         for (int c = 0; c < kCh; ++c) {
           const int qi = b < n_live ? s.qi_s[b * NQ + 32 * c + lane] : -1;
@@ -425,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
 #pragma unroll
-      for (int b = 0; b < kItemBufs; ++b) {
+      for (int b = 0; b < kSB; ++b) {
 #pragma unroll
         for (int c = 0; c < kCh; ++c) {
           const int e = b * NQ + 32 * c + lane;
@@ -460,11 +483,15 @@ __global__ void __launch_bounds__(kThreads, 1)
       load_pair(nx2);                                          // item i+2 (its record arrived last iteration)
       load_tau(nx1, tau_nx1);                                  // item i+1
 
-      const int islot = (int)(icount % kItemBufs);
+      const int islot = (int)(icount % kSB);         // item-state slot
+      const int qslot = (int)(icount % kItemBufs);   // query-buffer slot
       {
-        const unsigned par = ((icount / kItemBufs) & 1u) ^ 1u;
+        const unsigned par = ((icount / kSB) & 1u) ^ 1u;
+        const unsigned qpar = ((icount / kItemBufs) & 1u) ^ 1u;
         ROLE_TIC();
-        while (!mbar_try_wait_short(&s.q_empty[islot], par)) refresh(icount < kItemBufs ? (int)icount : kItemBufs);
+        while (!mbar_try_wait_short(&s.q_empty[islot], par)) refresh(icount < kSB ? (int)icount : kSB);
+        if (!WIDE)  // (WIDE: no query buffers, the queries travel with the row tiles)
+          while (!mbar_try_wait_short(&s.qb_empty[qslot], qpar)) refresh(icount < kSB ? (int)icount : kSB);
         ROLE_TOC(0);
       }
       const TcItem rec = cur.rec;
@@ -472,7 +499,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) {
           s.itm[islot].nq = 0;  // end of work
           mbar_arrive(&s.itm_full[islot]);
-          mbar_arrive(&s.q_full[islot]);
         }
         break;
       }
@@ -492,14 +518,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (lane == 0) s.itm[islot] = rec;
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&s.itm_full[islot]);  // the streamer starts on the row tiles
-        if (WIDE) {
-          mbar_arrive(&s.q_full[islot]);  // only the item's state: the queries travel with the row tiles
-        } else {
-          mbar_arrive_expect_tx(&s.q_full[islot], (unsigned)kblocks * kQBytes);
-          unsigned char* qdst = s.qbuf + (size_t)islot * kblocks * kQBytes;
+        mbar_arrive(&s.itm_full[islot]);  // the streamer starts on the row tiles, the filter sees the thresholds
+        if (!WIDE) {
+          mbar_arrive_expect_tx(&s.qb_full[qslot], (unsigned)kblocks * kQBytes);
+          unsigned char* qdst = s.qbuf + (size_t)qslot * kblocks * kQBytes;
           for (int kb = 0; kb < kblocks; ++kb)
-            tma_load_2d(qdst + kb * kQBytes, &map_q, kb * kTcBK, rec.pair_base, &s.q_full[islot]);
+            tma_load_2d(qdst + kb * kQBytes, &map_q, kb * kTcBK, rec.pair_base, &s.qb_full[qslot]);
         }
       }
       __syncwarp();
@@ -510,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       nx1 = nx2;
       nx2.rec = rec3;
     }
-    ROLE_REPORT(6);  // wait q_empty (threshold refresh rounds included), -, -, -, total
+    ROLE_REPORT(6);  // wait q_empty + qb_empty (threshold refresh rounds included), -, -, -, total
   } else if (warp == kStreamWarp) {
     // =================================== tile streamer ====================================
     if (lane == 0) {
@@ -519,8 +543,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       unsigned icount = 0, tcount = 0;
       const long long n_rows4 = a.n_rows & ~3ll;
       while (true) {
-        const int islot = (int)(icount % kItemBufs);
-        ROLE_WAIT(0, &s.itm_full[islot], (icount / kItemBufs) & 1u);
+        const int islot = (int)(icount % kSB);
+        ROLE_WAIT(0, &s.itm_full[islot], (icount / kSB) & 1u);
         const TcItem rec = s.itm[islot];
         if (rec.nq == 0) break;
         const int n_tiles = (rec.row1 - rec.row0 + kTile - 1) / kTile;
@@ -580,15 +604,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       unsigned sl = 0, sl_par = 0;  // slot ring position and the parity of its current round
       unsigned icount = 0, tcount = 0;
       while (true) {
-        const int islot = (int)(icount % kItemBufs);
-        ROLE_WAIT(0, &s.q_full[islot], (icount / kItemBufs) & 1u);
+        const int islot = (int)(icount % kSB);
+        const int qslot = (int)(icount % kItemBufs);
+        ROLE_WAIT(0, &s.itm_full[islot], (icount / kSB) & 1u);
         const int nq = s.itm[islot].nq;
         if (nq == 0) break;
         const int n_tiles = (s.itm[islot].row1 - s.itm[islot].row0 + kTile - 1) / kTile;
-        const unsigned char* qsrc = s.qbuf + (size_t)islot * kblocks * kQBytes;
+        if (!WIDE) ROLE_WAIT(0, &s.qb_full[qslot], (icount / kItemBufs) & 1u);
+        const unsigned char* qsrc = s.qbuf + (size_t)qslot * kblocks * kQBytes;
         for (int t = 0; t < n_tiles; ++t, ++tcount) {
-          const unsigned set = tcount % kSets;
-          ROLE_WAIT(1, &s.acc_empty[set], ((tcount / kSets) & 1u) ^ 1u);  // the filter drained this set
+          const unsigned set = tcount & sets_mask;
+          ROLE_WAIT(1, &s.acc_empty[set], ((tcount >> sets_log2) & 1u) ^ 1u);  // the filter drained this set
           tc_fence_after();
           const uint32_t acc = tmem_base + set * (uint32_t)NQ;
           for (int kb = 0; kb < kblocks; ++kb) {
@@ -609,9 +635,10 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           tc_commit(&s.acc_full[set]);
         }
+        if (!WIDE) tc_commit(&s.qb_empty[qslot]);  // the item's query buffer may be refilled
         ++icount;
       }
-      ROLE_REPORT(11);  // wait q_full, acc_empty, slot full, -, total
+      ROLE_REPORT(11);  // wait itm_full + qb_full, acc_empty, slot full, -, total
     }
     __syncwarp();
   } else {
@@ -649,23 +676,23 @@ __global__ void __launch_bounds__(kThreads, 1)
     // the queue's front has passed the item's last entry - after the next full batch as a rule, and by
     // scoring a partial batch only when the warp would otherwise wait (nothing is published to filter)
     unsigned enq_total = 0, done_total = 0;  // entries queued / scored so far
-    unsigned wm[kItemBufs + 1];              // enq_total at the end of each filtered, unreleased item
+    unsigned wm[kSB + 1];                    // enq_total at the end of each filtered, unreleased item (!QGLOBAL)
     int npend = 0;
     unsigned rel = 0;                        // item count of the oldest unreleased item
     auto release_ready = [&]() {
       while (npend > 0 && (int)(done_total - wm[0]) >= 0) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s.q_empty[rel % kItemBufs]);
+        if (lane == 0) mbar_arrive(&s.q_empty[rel % kSB]);
         ++rel;
         --npend;
 #pragma unroll
-        for (int i = 0; i < kItemBufs; ++i) wm[i] = wm[i + 1];
+        for (int i = 0; i < kSB; ++i) wm[i] = wm[i + 1];
       }
     };
     ROLE_T0();
     while (true) {
-      const int islot = (int)(icount % kItemBufs);
-      if (!QGLOBAL && npend > 0 && !mbar_try_wait_short(&s.q_full[islot], (icount / kItemBufs) & 1u)) {
+      const int islot = (int)(icount % kSB);
+      if (!QGLOBAL && npend > 0 && !mbar_try_wait_short(&s.itm_full[islot], (icount / kSB) & 1u)) {
         if (count > 0) {
           score_batch<METRIC, QGLOBAL, V8>(sc, q_row, q_meta, q_qi, head, count, lane, n_appended);
           head = (head + (unsigned)count) & (kQueueCap - 1);
@@ -675,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         release_ready();
       }
-      ROLE_WAIT(0, &s.q_full[islot], (icount / kItemBufs) & 1u);
+      ROLE_WAIT(0, &s.itm_full[islot], (icount / kSB) & 1u);
       const TcItem rec = s.itm[islot];
       if (rec.nq == 0) break;
       const float* th = s.thr_s + islot * NQ;
@@ -699,8 +726,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           ra = -1.0f / fmaxf(sqrtf(xn), 1e-8f);
           rb = 0.f;
         }
-        const unsigned set = tcount % kSets;
-        ROLE_WAIT(2, &s.acc_full[set], (tcount / kSets) & 1u);
+        const unsigned set = tcount & sets_mask;
+        ROLE_WAIT(2, &s.acc_full[set], (tcount >> sets_log2) & 1u);
         tc_fence_after();
         unsigned masks[kCh];
 #pragma unroll
@@ -770,7 +797,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) mbar_arrive(&s.q_empty[islot]);
       } else {
 #pragma unroll
-        for (int i = 0; i <= kItemBufs; ++i)
+        for (int i = 0; i <= kSB; ++i)
           if (i == npend) wm[i] = enq_total;
         ++npend;
         release_ready();
@@ -781,7 +808,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       score_batch<METRIC, QGLOBAL, V8>(sc, q_row, q_meta, q_qi, head, count, lane, n_appended);
       ++n_flush;
     }
-    ROLE_REPORT(16);  // (sum over the 8 filter warps) wait q_full, meta_full, acc_full, full-batch scoring, total
+    ROLE_REPORT(16);  // (sum over the 8 filter warps) wait itm_full, meta_full, acc_full, full-batch scoring, total
     if (a.stats != nullptr) {
       // debug counters: [0] survivors of the filter, [1] full batches, [2] end-of-item batches,
       // [3] candidates appended (n_appended is per lane), [4] tiles this warp filtered
@@ -1145,10 +1172,11 @@ int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {
   const bool wide = a.kblocks > kMaxKBlocks || a.nq_group == kTcNQMax;
   // Scorer query source.  The item's shared-memory copy halves the scorer's L2 requests (a survivor then costs
   // its 512-byte row alone) but ties queue entries to item slots: fine when an item yields a batch or more per
-  // warp (buckets of >= 8 tiles), while on 8-GPU shards (2 - 3 tiles per bucket) warps would sit on several
+  // warp (buckets of >= 16 tiles; config 3's 9-tile buckets measured 0.22 ms global against 0.26 shared, config 4's
+  // 19-tile buckets 0.89 against 0.87), while on 8-GPU shards (2 - 3 tiles per bucket) warps would sit on several
   // unreleased items, so short items take the pair-ordered global copy (QGLOBAL) - as wide rows must.
   // NLSH_TC_QGLOBAL=0/1 overrides (A/B runs).
-  bool qglobal = wide || a.avg_item_rows < 8 * kTile;
+  bool qglobal = wide || a.avg_item_rows < 16 * kTile;
   if (const char* env = getenv("NLSH_TC_QGLOBAL")) qglobal = wide || atoi(env) != 0;
   int n_slots = kMaxSlots;
   // each K block's slot is freed by its own tcgen05.commit, so any ring depth >= 2 makes progress.  With the
@@ -1165,6 +1193,14 @@ int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {
     if (v >= 3 && v <= kMaxSlots && scan_tc_smem(a.kblocks, v, wide, a.nq_group) <= 227 * 1024) n_slots = v;
   }
   a.n_slots = n_slots;
+  // Tiles between the TMA and the filter: slot ring + accumulator ring.  The scorer re-reads surviving rows from
+  // L2, and 148 SMs x 16 tiles x 64 KB in flight (150 MB) is more than the L2 holds, so the accumulator ring
+  // is used 8 deep by default (NLSH_TC_SETS=2/4/8/16: A/B runs).
+  a.sets_log2 = 3;
+  if (const char* env = getenv("NLSH_TC_SETS")) {
+    const int v = atoi(env);
+    a.sets_log2 = v >= 16 ? 4 : (v >= 8 ? 3 : (v >= 4 ? 2 : 1));
+  }
   const size_t smem = scan_tc_smem(a.kblocks, n_slots, wide, a.nq_group);
   CUtensorMap map_x, map_x32, map_q;
   int rc;
@@ -1177,10 +1213,14 @@ int nlsh_scan_tc_launch(int metric, TcScanArgs a, cudaStream_t st) {
   if (const char* env = getenv("NLSH_TC_GRID")) grid = atoi(env);
   if (grid < 1) grid = 1;
   if (grid > nlsh_num_sms()) grid = nlsh_num_sms();
-  // 32-byte loads in the scorer when every row of xs and qs starts on a 32-byte boundary (NLSH_TC_V8=0: A/B runs)
-  bool v8 = a.d_pad % 8 == 0 && (reinterpret_cast<uintptr_t>(a.xs) & 31) == 0 &&
+  // 32-byte row loads in the scorer when the query comes from shared memory and every row of xs starts on a
+  // 32-byte boundary (with both operands from global memory they measured slower: shard 0.194 against 0.176 ms,
+  // config 5 3.83 against 3.72); NLSH_TC_V8=0/1 overrides (A/B runs)
+  bool v8 = !qglobal && a.d_pad % 8 == 0 && (reinterpret_cast<uintptr_t>(a.xs) & 31) == 0 &&
             (reinterpret_cast<uintptr_t>(a.qs) & 31) == 0;
-  if (const char* env = getenv("NLSH_TC_V8")) v8 = v8 && atoi(env) != 0;
+  if (const char* env = getenv("NLSH_TC_V8"))
+    v8 = atoi(env) != 0 && a.d_pad % 8 == 0 && (reinterpret_cast<uintptr_t>(a.xs) & 31) == 0 &&
+         (reinterpret_cast<uintptr_t>(a.qs) & 31) == 0;
   if (metric == NLSH_METRIC_L2)
     return launch_metric<NLSH_METRIC_L2>(a, map_x, map_x32, map_q, wide, qglobal, v8, grid, smem, st);
   return launch_metric<NLSH_METRIC_ANGULAR>(a, map_x, map_x32, map_q, wide, qglobal, v8, grid, smem, st);

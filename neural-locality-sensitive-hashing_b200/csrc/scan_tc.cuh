@@ -46,6 +46,7 @@ struct TcScanArgs {
   long long n_rows;
   long long n_pairs;
   int k, d, d_pad, kblocks, n_slots;
+  int sets_log2;         // log2 of the TMEM accumulator sets in use (tiles the MMAs may run ahead of the filter)
   int nq_group;          // queries per item: kTcNQ or kTcNQMax (the plan's group size)
   int avg_item_rows;     // average rows per bucket (chooses the scorer's query source)
   int sm_reserve;        // SMs the persistent grid leaves free (flags bits 8-15 of nlsh_query_scan_topk)

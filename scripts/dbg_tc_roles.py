@@ -36,10 +36,10 @@ ws = list(_native._workspaces.values())[0].buf
 B = 1 << hs
 st = ws.view(torch.uint8)[(2 * B + 2) * 4:(2 * B + 2) * 4 + 26 * 8].view(torch.int64).cpu().tolist()
 roles = {
-    "planner": (6, ["wait q_empty (threshold refresh rounds)", "-", "-", "-"]),
+    "planner": (6, ["wait q_empty + qb_empty (threshold refresh rounds)", "-", "-", "-"]),
     "streamer": (21, ["wait itm_full", "wait meta_empty", "wait slot empty", "-"]),
-    "mma": (11, ["wait q_full", "wait acc_empty", "wait slot full", "-"]),
-    "filter(8 warps)": (16, ["wait q_full", "wait meta_full", "wait acc_full", "scoring full batches"]),
+    "mma": (11, ["wait itm_full + qb_full", "wait acc_empty", "wait slot full", "-"]),
+    "filter(8 warps)": (16, ["wait itm_full", "wait meta_full", "wait acc_full", "scoring full batches"]),
 }
 out = {"workload": wl, "rows": n, "p": p, "scan_ms_instrumented": ms, "pairs": int(nc.long().sum()),
        "survivors": st[0], "full_batches": st[1], "end_batches": st[2], "candidates": st[3]}

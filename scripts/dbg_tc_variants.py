@@ -25,7 +25,7 @@ Q = synth.make_queries(nq, d, hs, seed, dev, sep=bench.SEP)
 hashing, _ = bench.make_hashing(d, hs, metric, seed, dev, 300)
 idx = Indexer(hashing, X, hashing.distance, metric=metric)
 probes = idx.hash_tensors(Q, p)
-SWITCHES = ("NLSH_TC_NQ", "NLSH_TC_QGLOBAL", "NLSH_TC_GRID", "NLSH_TC_SLOTS", "NLSH_SCAN_SEED", "NLSH_SCAN_SEED_DIV", "NLSH_TC_LADDER", "NLSH_TC_CAND_CAP", "NLSH_SCAN_IMPL",
+SWITCHES = ("NLSH_TC_SETS", "NLSH_TC_NQ", "NLSH_TC_QGLOBAL", "NLSH_TC_GRID", "NLSH_TC_SLOTS", "NLSH_SCAN_SEED", "NLSH_SCAN_SEED_DIV", "NLSH_TC_LADDER", "NLSH_TC_CAND_CAP", "NLSH_SCAN_IMPL",
             "NLSH_TC_STATS", "NLSH_TC_V8", "NLSH_TC_SMEM_KB")
 VARIANTS = [{}] + [dict(kv.split("=") for kv in v.split(",")) for v in os.environ.get(
     "TC_VARIANTS", "NLSH_TC_LADDER=0;NLSH_SCAN_SEED=128;NLSH_SCAN_SEED=256;NLSH_SCAN_SEED=512;NLSH_TC_SLOTS=6;"

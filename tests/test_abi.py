@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     from nlsh import _native
-    assert _native.lib().nlsh_version() == 300
+    assert _native.lib().nlsh_version() == 310
     assert isinstance(_native.last_error(), str)
 
 
