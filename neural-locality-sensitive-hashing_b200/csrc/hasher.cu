@@ -232,22 +232,22 @@ __global__ void __launch_bounds__(128)
   const int n_masks = 1 << n_sel;
   for (int m0 = 0; m0 < n_masks; m0 += 32) {
     const int mc = m0 + lane;  // compact mask over the selected bits (ascending position)
-    // cost of the mask = sum of its bits' costs, added from the highest position down (the order of the full
-    // enumeration in oracle.topp_probes, so equal sums are bit-equal); bit j of mc = j-th selected position
     float cost = 0.f;
     int full = 0;
-    for (int j = n_sel - 1; j >= 0; --j) {  // warp-uniform
-      const int pos = __fns(sel, 0, j + 1);
-      const float c = __shfl_sync(NLSH_FULL_MASK, my_cost, pos);
-      if ((mc >> j) & 1) {
-        cost = __fadd_rn(cost, c);
-        full |= 1 << pos;
+#pragma unroll
+    for (int i = 0; i < NLSH_MAX_HASH_BITS; ++i) {
+      if (i < hs) {
+        const int pos = hs - 1 - i;
+        if ((sel >> pos) & 1u) {
+          const int j = __popc(sel & ((1u << pos) - 1u));
+          if ((mc >> j) & 1) {
+            cost = __fadd_rn(cost, a[i]);
+            full |= 1 << pos;
+          }
+        }
       }
     }
-    if (m0 == 0)  // the first 32 masks: one bitonic sort instead of p inserts into the empty list
-      top.seed32(cost, full, mc < n_masks, NLSH_ID_SENTINEL, p);
-    else
-      top.offer(cost, full, mc < n_masks, p);
+    top.offer(cost, full, mc < n_masks, p);
   }
 #pragma unroll
   for (int j = 0; j < KPL; ++j) {
