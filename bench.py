@@ -167,15 +167,18 @@ class ClockSampler:
         return out
 
 
-def timed_steps(step_fn, steps, barrier):
+def timed_steps(step_fn, steps, barrier, finish=None):
     """EXACTLY `steps` calls bracketed by barrier + synchronize, timed with CUDA events on the
-    launching stream; returns this rank's elapsed ms."""
+    launching stream; returns this rank's elapsed ms.  `finish` (the serving loop's fence) orders the
+    launching stream after everything the steps submitted to other streams, inside the timed region."""
     barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         step_fn()
+    if finish is not None:
+        finish()
     e1.record()
     torch.cuda.synchronize()
     barrier()
@@ -310,10 +313,9 @@ def run_b200(args):
         pipe = PipelinedSearch(index, nq, k=k, hash_times=p_used, depth=lanes, to_host=False)
         kernels_per_batch = pipe.kernels_per_call
 
-        def step():
+        def step():  # the lanes stay full across steps: the fence comes once, before the closing event
             for _ in range(nb):
                 pipe.submit(Q)
-            pipe.fence()
         # the pipelined loop returns what the serial call returns
         t = pipe.submit(Q)
         p_ids, p_d, _ = pipe.result(t)
@@ -322,10 +324,13 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    finish = pipe.fence if pipe is not None else None
     for _ in range(max(args.warmup, 3)):
         step()
+    if finish is not None:
+        finish()
     launches0 = _native.kernel_launch_count()
-    ms = max_over_ranks(timed_steps(step, args.steps, barrier), device)
+    ms = max_over_ranks(timed_steps(step, args.steps, barrier, finish), device)
     launches = _native.kernel_launch_count() - launches0
     if kernels_per_batch is not None:  # graph replays do not pass through the counter
         launches = kernels_per_batch * nb * args.steps
