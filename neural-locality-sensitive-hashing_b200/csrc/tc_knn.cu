@@ -194,12 +194,14 @@ __global__ void __launch_bounds__(kKnMaxThreads, 1)
   if (warp == 0) {
     // ------------------------------- TMA producer ---------------------------------------
     if (lane == 0) {
-      unsigned ring = 0;
+      // running stage index / round parity: `ring % stages` with a run-time divisor is a 200-cycle dependent
+      // chain per K block in this single-thread role (measured in scan_tc.cu's producer)
+      int s = 0;
+      unsigned par = 0;
       for (int j = 0; j < n_tiles; ++j) {
         const int row0 = (tile0 + j) * kKnBN;
-        for (int kb = 0; kb < a.kblocks; ++kb, ++ring) {
-          const int s = (int)(ring % (unsigned)a.stages);
-          mbar_wait(&empty_bar[s], ((ring / (unsigned)a.stages) & 1u) ^ 1u);
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+          mbar_wait_poll(&empty_bar[s], par ^ 1u);
           unsigned char* st = base + (size_t)s * kKnStageBytes;
           const unsigned extra = kb == 0 ? (unsigned)(kKnBN * sizeof(float)) : 0u;
           mbar_arrive_expect_tx(&full_bar[s], kKnStageBytes + extra);
@@ -208,6 +210,10 @@ __global__ void __launch_bounds__(kKnMaxThreads, 1)
           if (kb == 0)
             bulk_g2s(norm_ring + (j % kKnNormSlots) * kKnBN, a.xterm + row0, kKnBN * sizeof(float),
                      &full_bar[s]);
+          if (++s == a.stages) {
+            s = 0;
+            par ^= 1u;
+          }
         }
       }
     }
@@ -216,16 +222,16 @@ __global__ void __launch_bounds__(kKnMaxThreads, 1)
     // ------------------------------- MMA issuer -----------------------------------------
     if (lane == 0) {
       const uint32_t idesc = make_tf32_idesc(kKnBN);
-      unsigned ring = 0;
+      int s = 0;
+      unsigned par = 0;
       for (int j = 0; j < n_tiles; ++j) {
         const int set = j & 1;
-        mbar_wait(&acc_empty[set], (((unsigned)j >> 1) & 1u) ^ 1u);  // epilogue drained this set
+        mbar_wait_poll(&acc_empty[set], (((unsigned)j >> 1) & 1u) ^ 1u);  // epilogue drained this set
         tc_fence_after();
         const uint32_t acc_main = tmem_base + 256u + (uint32_t)(set * 128);
         const uint32_t acc_cross = acc_main + 64u;
-        for (int kb = 0; kb < a.kblocks; ++kb, ++ring) {
-          const int s = (int)(ring % (unsigned)a.stages);
-          mbar_wait(&full_bar[s], (ring / (unsigned)a.stages) & 1u);
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+          mbar_wait_poll(&full_bar[s], par);
           tc_fence_after();
           unsigned char* st = base + (size_t)s * kKnStageBytes;
           const uint64_t db_hi = make_kmajor_sw128_desc(st);
@@ -240,6 +246,10 @@ __global__ void __launch_bounds__(kKnMaxThreads, 1)
             tc_mma_tf32_ts(acc_cross, a_lo, db_hi + adv, idesc, 1u);
           }
           tc_commit(&empty_bar[s]);
+          if (++s == a.stages) {
+            s = 0;
+            par ^= 1u;
+          }
         }
         tc_commit(&acc_full[set]);
       }
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(kKnMaxThreads, 1)
     const int c_lo = cg * ncols;
     for (int j = 0; j < n_tiles; ++j) {
       const int set = j & 1;
-      mbar_wait(&acc_full[set], ((unsigned)j >> 1) & 1u);
+      mbar_wait_poll(&acc_full[set], ((unsigned)j >> 1) & 1u);
       tc_fence_after();
       const uint32_t acc_main = lane_base + 256u + (uint32_t)(set * 128);
       const float* xt = norm_ring + (j % kKnNormSlots) * kKnBN;

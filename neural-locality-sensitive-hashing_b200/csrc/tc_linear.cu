@@ -85,15 +85,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 4) {
     // ------------------------------- TMA producer ---------------------------------------
     if (lane == 0) {
+      int s = 0;
+      unsigned par = 0;  // running stage / round parity instead of a run-time modulo per K block
       for (int kb = 0; kb < n_kblocks; ++kb) {
-        const int s = kb % a.stages;
-        mbar_wait(&empty_bar[s], (((unsigned)kb / (unsigned)a.stages) & 1u) ^ 1u);
+        mbar_wait_poll(&empty_bar[s], par ^ 1u);
         mbar_arrive_expect_tx(&full_bar[s], (unsigned)stage_bytes);
         unsigned char* st = base + (size_t)s * stage_bytes;
         tma_load_2d(st, &map_a_hi, kb * kTcBK, m0, &full_bar[s]);
         tma_load_2d(st + a_bytes, &map_a_lo, kb * kTcBK, m0, &full_bar[s]);
         tma_load_2d(st + 2 * a_bytes, &map_w_hi, kb * kTcBK, 0, &full_bar[s]);
         tma_load_2d(st + 2 * a_bytes + w_bytes, &map_w_lo, kb * kTcBK, 0, &full_bar[s]);
+        if (++s == a.stages) {
+          s = 0;
+          par ^= 1u;
+        }
       }
     }
     __syncwarp();
@@ -101,9 +106,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // ------------------------------- MMA issuer -----------------------------------------
     if (lane == 0) {
       const uint32_t idesc = make_tf32_idesc(a.n_pad);
+      int s = 0;
+      unsigned par = 0;
       for (int kb = 0; kb < n_kblocks; ++kb) {
-        const int s = kb % a.stages;
-        mbar_wait(&full_bar[s], ((unsigned)kb / (unsigned)a.stages) & 1u);
+        mbar_wait_poll(&full_bar[s], par);
         tc_fence_after();
         unsigned char* st = base + (size_t)s * stage_bytes;
         const uint64_t da_hi = make_kmajor_sw128_desc(st);
@@ -120,13 +126,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           tc_mma_tf32(acc_cross, da_lo + adv, dw_hi + adv, idesc, 1u);
         }
         tc_commit(&empty_bar[s]);  // the stage may be refilled once these MMAs have read it
+        if (++s == a.stages) {
+          s = 0;
+          par ^= 1u;
+        }
       }
       tc_commit(acc_bar);  // accumulator complete
     }
     __syncwarp();
   } else {
     // ------------------------------- epilogue (warps 0-3) -------------------------------
-    mbar_wait(acc_bar, 0);
+    mbar_wait_poll(acc_bar, 0);
     tc_fence_after();
     const int row = m0 + warp * 32 + lane;  // TMEM lane = accumulator row
     const bool row_ok = row < a.M;
