@@ -207,6 +207,12 @@ int nlsh_query_seed_tau(const float* xq, int64_t n_queries, int32_t d, const int
                         const int32_t* offsets, int32_t n_buckets, const float* x_sorted, int64_t n_rows,
                         int32_t metric, int32_t k, float* tau_out, void* workspace, size_t workspace_bytes,
                         void* stream);
+/* The same with the base sample size chosen by the caller (sample_rows rows of the query's first probed
+ * bucket(s), 0 = the library's rule): a rank that seeds only its 1/N slice of the queries affords more rows. */
+int nlsh_query_seed_tau_rows(const float* xq, int64_t n_queries, int32_t d, const int32_t* probes, int32_t p,
+                             const int32_t* offsets, int32_t n_buckets, const float* x_sorted, int64_t n_rows,
+                             int32_t metric, int32_t k, int32_t sample_rows, float* tau_out, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* Which kernel nlsh_query_scan_topk runs for this shape with / without x_sqnorm and default flags:
  * 1 = tensor-core filtered scan (scan_tc.cu: d <= 4096, k <= 128 and at least ~4 (query, probe) pairs

@@ -1432,10 +1432,11 @@ extern "C" size_t nlsh_query_seed_workspace_bytes(int64_t n_queries, int32_t d) 
   return ws.total();
 }
 
-extern "C" int nlsh_query_seed_tau(const float* xq, int64_t n_queries, int32_t d, const int32_t* probes,
-                                   int32_t p, const int32_t* offsets, int32_t n_buckets,
+extern "C" int nlsh_query_seed_tau_rows(const float* xq, int64_t n_queries, int32_t d, const int32_t* probes,
+                                        int32_t p, const int32_t* offsets, int32_t n_buckets,
                                    const float* x_sorted, int64_t n_rows, int32_t metric, int32_t k,
-                                   float* tau_out, void* workspace, size_t workspace_bytes, void* stream) {
+                                   int32_t sample_rows, float* tau_out, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
   NLSH_REQUIRE(n_queries >= 0 && d >= 1 && d <= 16384 && p >= 1 && p <= 1024, "seed: bad shape");
   NLSH_REQUIRE(k >= 1 && k <= NLSH_MAX_K, "seed: k=%d outside [1, %d]", k, NLSH_MAX_K);
   NLSH_REQUIRE(n_buckets >= 1 && n_buckets <= (1 << 20), "seed: n_buckets=%d outside [1, 2^20]", n_buckets);
@@ -1457,8 +1458,17 @@ extern "C" int nlsh_query_seed_tau(const float* xq, int64_t n_queries, int32_t d
   prepare_queries_kernel<<<(unsigned)((n_queries + 3) / 4), 128, 0, st>>>(
       xq, n_queries, d, d_pad, metric == NLSH_METRIC_ANGULAR ? 1 : 0, qn);
   NLSH_CUDA_TRY(nlsh_post_launch());
+  NLSH_REQUIRE(sample_rows >= 0 && sample_rows <= 4096, "seed: sample_rows=%d outside [0, 4096]", sample_rows);
   return nlsh_scan_tc_seed(qn, n_queries, probes, p, offsets, x_sorted, n_rows, n_buckets, d, d_pad, k, metric,
-                           tau_g, tau_out, st);
+                           tau_g, tau_out, st, sample_rows);
+}
+
+extern "C" int nlsh_query_seed_tau(const float* xq, int64_t n_queries, int32_t d, const int32_t* probes,
+                                   int32_t p, const int32_t* offsets, int32_t n_buckets,
+                                   const float* x_sorted, int64_t n_rows, int32_t metric, int32_t k,
+                                   float* tau_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return nlsh_query_seed_tau_rows(xq, n_queries, d, probes, p, offsets, n_buckets, x_sorted, n_rows, metric, k, 0,
+                                  tau_out, workspace, workspace_bytes, stream);
 }
 
 extern "C" int nlsh_query_scan_topk(const float* xq, int64_t n_queries, int32_t d,

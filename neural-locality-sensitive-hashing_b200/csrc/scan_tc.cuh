@@ -60,7 +60,7 @@ bool nlsh_scan_tc_supported(int d, int k, int metric);
 // i < *n_valid, then the seed - or, with tau_seed != NULL, tau_g = tau0 = tau_seed (bounds from elsewhere).
 int nlsh_scan_tc_seed(const float* qn, long long n_queries, const int* probes, int p, const int* offsets,
                       const float* xs, long long n_rows, int n_buckets, int d, int d_pad, int k, int metric,
-                      float* tau_g, float* tau0, cudaStream_t st);
+                      float* tau_g, float* tau0, cudaStream_t st, int sample_rows = 0);
 int nlsh_scan_tc_prepare(const float* qn, const int* pairs, const int* n_valid, long long n_pairs,
                          int p, int d_pad, float* qs, int* pq, float* pqn2, float* tau_g, float* tau0,
                          const float* tau_seed, long long n_queries, const int* probes, const int* offsets,

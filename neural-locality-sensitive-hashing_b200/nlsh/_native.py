@@ -71,6 +71,8 @@ PROTOTYPES = {
     "nlsh_query_seed_workspace_bytes": (_sz, [_i64, _i32]),
     "nlsh_query_seed_tau": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _i64, _i32, _i32, _vp, _vp,
                                            _sz, _vp]),
+    "nlsh_query_seed_tau_rows": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _i64, _i32, _i32, _i32,
+                                                _vp, _vp, _sz, _vp]),
     "nlsh_query_scan_impl": (ctypes.c_int, [_i32, _i32, _i32, _i32, _i64, _i32, _i32]),
     "nlsh_knn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "nlsh_knn_bruteforce": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _i64,
@@ -344,9 +346,10 @@ def build_csr(codes, n_buckets, x=None, want_sqnorm=False, workspace=None):
 # --------------------------------------------------------------------------------------
 # query / kNN / merge
 # --------------------------------------------------------------------------------------
-def query_seed_tau(xq, probes, offsets, x_sorted, d, metric, k, workspace=None):
+def query_seed_tau(xq, probes, offsets, x_sorted, d, metric, k, workspace=None, sample_rows=0):
     """Distance bounds fp32 [Q] of the queries from a sample of the rows of their probed buckets (the seed of
-    the tensor-core scan's filter); valid for any shard of the same database (query_scan_topk(tau_seed=...))."""
+    the tensor-core scan's filter); valid for any shard of the same database (query_scan_topk(tau_seed=...)).
+    sample_rows: base sample size (0 = the library's rule)."""
     xq = _f32c(xq, "query_vectors")
     require_cuda(probes, "probes")
     probes = probes.to(torch.int32).contiguous()
@@ -355,10 +358,10 @@ def query_seed_tau(xq, probes, offsets, x_sorted, d, metric, k, workspace=None):
     with torch.cuda.device(xq.device):
         nbytes = lib().nlsh_query_seed_workspace_bytes(nq, d)
         ws = _workspace(xq.device, nbytes, workspace)
-        rc = lib().nlsh_query_seed_tau(_ptr(xq), nq, d, _ptr(probes), probes.shape[1], _ptr(offsets),
-                                       offsets.shape[0] - 1, _ptr(x_sorted), x_sorted.shape[0], metric, k,
-                                       _ptr(tau), _ptr(ws), ws.numel(), _stream())
-    _check(rc, "nlsh_query_seed_tau")
+        rc = lib().nlsh_query_seed_tau_rows(_ptr(xq), nq, d, _ptr(probes), probes.shape[1], _ptr(offsets),
+                                            offsets.shape[0] - 1, _ptr(x_sorted), x_sorted.shape[0], metric, k,
+                                            int(sample_rows), _ptr(tau), _ptr(ws), ws.numel(), _stream())
+    _check(rc, "nlsh_query_seed_tau_rows")
     return tau
 
 

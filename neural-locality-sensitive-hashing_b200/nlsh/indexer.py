@@ -206,12 +206,12 @@ class Indexer:
         return codes_to_sets(self.hash_tensors(query_vectors, hash_times))
 
     # ---- query ---------------------------------------------------------------------------
-    def seed_tau_tensors(self, query_vectors, probes, k=10, workspace=None):
+    def seed_tau_tensors(self, query_vectors, probes, k=10, workspace=None, sample_rows=0):
         """Distance bounds fp32 [Q] of the queries from a sample of this index's rows (see
         _native.query_seed_tau): upper bounds of the k-th best distance over ANY index that holds these rows,
         so a row-sharded search seeds each query on one rank only."""
         return _native.query_seed_tau(query_vectors, probes, self._offsets, self._x_sorted, self._dim,
-                                      self._metric, k, workspace=workspace)
+                                      self._metric, k, workspace=workspace, sample_rows=sample_rows)
 
     def uses_tensor_core_scan(self, n_queries, k, hash_times):
         return _native.scan_impl(self._dim, k, self._metric, self._x_sqnorm is not None, n_queries, hash_times,

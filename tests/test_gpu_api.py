@@ -100,9 +100,11 @@ def test_bounds_seeded_on_one_shard_serve_every_shard(monkeypatch, metric, d, k)
     for r in range(G):
         lo, hi = shard_range(n, r, G)
         shards.append(Indexer(hashing, X[lo:hi], None, metric=metric, id_offset=lo))
-    for seeder in (0, G - 1):
-        tau = shards[seeder].seed_tau_tensors(Q, probes, k)
+    for seeder, rows in ((0, 0), (G - 1, 0), (1, 192)):  # rows: the caller's sample size (nlsh_query_seed_tau_rows)
+        tau = shards[seeder].seed_tau_tensors(Q, probes, k, sample_rows=rows)
         assert tau.shape == (nq,) and tau.dtype == torch.float32
+        if rows:  # a larger sample can only tighten the bound
+            assert (tau <= shards[seeder].seed_tau_tensors(Q, probes, k)).all()
         # a valid bound: at least the exact k-th best distance over the whole database (squared for L2)
         kth = f_d[:, k - 1] ** 2 if metric == "l2" else f_d[:, k - 1]
         assert (tau >= kth).all()
