@@ -31,35 +31,42 @@
 // ladder[query][l] (one atomicAdd), and as soon as the levels >= l hold k candidates, t_l is an upper
 // bound of the k-th best distance and goes into tau_g (atomicMin).  Lock-free, order-independent (any k
 // candidates bound the k-th best), shared by all probes of a query on all SMs; an item reads tau_g
-// when the producer picks it up.  There are no per-item lists and nothing in the kernel waits for a
+// when the planner picks it up and again whenever the planner waits.  There are no per-item lists and nothing in the kernel waits for a
 // threshold: the stages below only hand tiles forward.
 //
-// Roles in a CTA (one persistent CTA per SM, 320 threads):
-//   warp 0         producer: owns the work queue (atomic counter), looks four items ahead (item index ->
-//                  record -> per-pair query index / norm -> tau_g, one dependent load per iteration, so
-//                  none of these latencies is exposed).  Per item the 32 lanes publish the per-query
-//                  state (threshold, query index) to shared memory, lane 0 TMA-loads the
-//                  item's queries (box 32 rows x 32 fp32 per K block, SWIZZLE_128B; 4-deep item ring)
-//                  and streams the row tiles (box 128 rows x 32 fp32; 32-row boxes for the ragged last
-//                  tile of a bucket) into the slot ring, row norms alongside (bulk copy);
-//   warp 1 lane 0  MMA issuer: per tile and K block 4 x tcgen05.mma M128 N32 K8 into one of 16
-//                  TMEM accumulator sets; tcgen05.commit frees the slot, the last one of a tile
-//                  signals acc_full - a slot lives from its TMA issue to the end of its MMAs, and the
-//                  accumulator ring lets the front end run that many tiles ahead of the filter;
+// Roles in a CTA (one persistent CTA per SM, 352 threads; mbarrier hand-offs only):
+//   warp 0         planner (32 lanes): owns the work queue (one atom.global.add per item, its result consumed an
+//                  iteration later), looks four items ahead (item index -> record -> per-pair query index / norm
+//                  -> tau_g, one dependent load per iteration, so none of these latencies is exposed), publishes
+//                  the per-query state (threshold, bound, query index) to the item-state ring, TMA-loads the item's
+//                  queries (box 32 rows x 32 fp32 per K block, SWIZZLE_128B; the B operand) into the query-buffer
+//                  ring and, whenever it has to wait for a ring slot, re-reads tau_g for the queries of the items in
+//                  flight and rewrites the thresholds that got lower;
+//   warp 10 lane 0 tile streamer: for every published item the row tiles (box 128 rows x 32 fp32 per K block;
+//                  32-row boxes for the ragged last tile of a bucket) into the slot ring, row norms alongside
+//                  (bulk copy).  Nothing but mbarrier waits and TMA issues, running slot / parity counters: the
+//                  single producer warp that used to do the planner's work too was busy - not waiting - 90 % of
+//                  the time (a run-time `ring % n_slots` alone is a 200-cycle dependent chain per K block);
+//   warp 1 lane 0  MMA issuer: per tile and K block 4 x tcgen05.mma M128 N32 K8 into one of 16 TMEM accumulator
+//                  sets (8 in use by default: with 16 the tiles between the TMA and the filter are more than the
+//                  L2 holds, and the scorer re-reads rows from L2); tcgen05.commit frees the slot, the last one of
+//                  a tile signals acc_full, the one after an item's last tile frees its query buffer;
 //   warps 2-9      filter + score, two groups of four (one warp per TMEM lane quarter), group g takes
 //                  the tiles with tile index = g (mod 2): tcgen05.ld the row's 32 scores (then the TMEM
 //                  set is free again), bound + compare, survivors go to the warp's PRIVATE queue in
-//                  shared memory (no atomics); whenever 32 are queued - and at the end of an item, whose
-//                  queries leave shared memory then - the warp scores them one per lane: the row is
-//                  re-read from L2 (it has just streamed through), the query comes from the item's
-//                  shared-memory copy, candidates within the bound are appended to the query's buffer.
+//                  shared memory (no atomics); whenever 32 are queued the warp scores them one per lane
+//                  (score_batch): id, bound and ladder scale are requested first, the row is re-read from L2
+//                  (it has just streamed through), candidates within the bound are appended to the query's
+//                  buffer, the append's round trip overlaps the ladder's.
 //
-// Variants (template parameters): QGLOBAL - the scorer reads the query from the pair-ordered global copy
-// instead of the item's shared-memory copy; queue entries then do not refer to an item slot and nothing
-// is flushed at the end of an item (buckets of two or three tiles: 8-GPU shards).  WIDE (d_pad > 128,
-// config 5's 960-wide rows) - the queries do not fit shared memory, so the K block of the item's queries
-// travels with each K block of a row tile (a 20 KB slot: 16 KB rows + 4 KB queries, both by TMA; the queries
-// come from L2), the accumulate runs over d_pad / 32 K blocks, and the scorer is QGLOBAL.
+// Variants (template parameters): QGLOBAL - the scorer reads the query from the pair-ordered global copy; queue
+// entries then do not refer to an item slot (buckets of a few tiles: 8-GPU shards; wide rows).  Otherwise the
+// query comes from the item's shared-memory copy (half the scorer's L2 requests): a queue entry pins its item
+// slot, which is released when the queue's front has passed the item's last entry - a partial batch is scored
+// only when the warp would otherwise block.  WIDE (d_pad > 128, config 5's 960-wide rows, or 128 queries per
+// item) - the queries do not fit shared memory, so the K block of the item's queries travels with each K block
+// of a row tile (both by TMA; the queries come from L2), the accumulate runs over d_pad / 32 K blocks, and the
+// scorer is QGLOBAL.  V8 - the scorer reads rows 32 bytes per load (LDG.256, not allocated in L1).
 #include <stdlib.h>
 #include <string.h>
 
