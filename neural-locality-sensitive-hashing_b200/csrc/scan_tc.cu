@@ -342,8 +342,16 @@ __device__ NLSH_SCORE_INLINE void score_batch(const ScoreCtx a, const int* q_row
   __syncwarp();
 }
 
+// NLSH_TC_LB: the thread count the scan kernel is compiled for (it always launches kThreads = 352) - a register cap
+// in disguise for A/B builds (`make variant NAME=r128 DEFS=-DNLSH_TC_LB=512`: 128 registers, 12 - 112 bytes of
+// spills).  The idea was to leave room on every SM for the small kernels of the next batch beside the persistent
+// scan CTA; measured, the lanes of nlsh.parallel.PipelinedSearch overlap no better (config 4: 1.131 against 1.133
+// ms per batch, shard-sized 0.370 against 0.367; profiles/r2_experiments/ab_scan_regcap.txt), so the default stays.
+#ifndef NLSH_TC_LB
+#define NLSH_TC_LB kThreads
+#endif
 template <int METRIC, int NQ, bool WIDE, bool QGLOBAL, bool V8>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(NLSH_TC_LB, 1)
     scan_tc_kernel(const TcScanArgs a, const __grid_constant__ CUtensorMap map_x,
                    const __grid_constant__ CUtensorMap map_x32, const __grid_constant__ CUtensorMap map_q) {
   static_assert(!WIDE || QGLOBAL, "wide rows: the queries are not resident in shared memory");
