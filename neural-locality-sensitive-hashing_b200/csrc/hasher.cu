@@ -16,7 +16,8 @@ int nlsh_tc_split(const float* x, size_t n, float* hi, float* lo, cudaStream_t s
 int nlsh_tc_linear(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo,
                    const float* bias, int M, int N, int K, int act, float act_scale, float* out_hi,
                    float* out_lo, float* out_full, int ld_out, int* codes_out, int head,
-                   cudaStream_t st);
+                   cudaStream_t st, const float* head_w = nullptr, const float* head_b = nullptr,
+                   int head_n = 0);
 
 namespace {
 
@@ -406,10 +407,17 @@ int mlp_hash_tc(const float* x, int64_t n, int32_t d, const nlsh_layer_t* layers
   for (int i = 0; i < 4; ++i) act[i] = ws.take<float>(p.act_floats);
   float* logits_tmp = ws.take<float>((size_t)p.chunk * p.hs);
 
+  // The output layer (out_dim = hash_size <= 16, no activation) rides in the epilogue of the layer before it
+  // (tc_linear.cu, "fused head") instead of being a tcgen05 layer of its own; NLSH_MLP_FUSE_HEAD=0: A/B runs.
+  bool fuse_head = n_layers >= 2 && layers[n_layers - 1].out_dim <= 16 &&
+                   layers[n_layers - 1].act == NLSH_ACT_IDENTITY &&
+                   layers[n_layers - 1].in_dim == layers[n_layers - 2].out_dim;
+  if (const char* env = getenv("NLSH_MLP_FUSE_HEAD")) fuse_head = fuse_head && atoi(env) != 0;
+  const int n_tc_layers = fuse_head ? n_layers - 1 : n_layers;
   // weights change between index builds while training: split them at every call (tiny)
   size_t w_off[NLSH_MAX_LAYERS];
   size_t off = 0;
-  for (int l = 0; l < n_layers; ++l) {
+  for (int l = 0; l < n_tc_layers; ++l) {
     w_off[l] = off;
     const size_t cnt = (size_t)layers[l].in_dim * layers[l].out_dim;
     int rc = nlsh_tc_split(layers[l].weight, cnt, w_hi + off, w_lo + off, st);
@@ -422,14 +430,17 @@ int mlp_hash_tc(const float* x, int64_t n, int32_t d, const nlsh_layer_t* layers
     if (rc != NLSH_OK) return rc;
     int cur = 0;  // act[cur], act[cur + 1] hold the split input of the next layer
     float* logits_chunk = logits_out ? logits_out + (size_t)r0 * p.hs : logits_tmp;
-    for (int l = 0; l < n_layers; ++l) {
-      const bool last = (l == n_layers - 1);
+    for (int l = 0; l < n_tc_layers; ++l) {
+      const bool last = (l == n_tc_layers - 1);
+      const bool fused = last && fuse_head;
+      const nlsh_layer_t& out_l = layers[n_layers - 1];
       const int nxt = cur ^ 2;
       rc = nlsh_tc_linear(act[cur], act[cur + 1], w_hi + w_off[l], w_lo + w_off[l], layers[l].bias,
                           rows, layers[l].out_dim, layers[l].in_dim, layers[l].act,
                           layers[l].act_scale, last ? nullptr : act[nxt], last ? nullptr : act[nxt + 1],
-                          last ? logits_chunk : nullptr, layers[l].out_dim,
-                          last && codes_out ? codes_out + r0 : nullptr, head, st);
+                          last ? logits_chunk : nullptr, fused ? out_l.out_dim : layers[l].out_dim,
+                          last && codes_out ? codes_out + r0 : nullptr, head, st,
+                          fused ? out_l.weight : nullptr, fused ? out_l.bias : nullptr, fused ? out_l.out_dim : 0);
       if (rc != NLSH_OK) return rc;
       cur = nxt;
     }

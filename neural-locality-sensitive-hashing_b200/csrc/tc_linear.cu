@@ -42,7 +42,17 @@ struct TcArgs {
   int stages;
   int n_main;         // TMEM accumulators for hi*hi (k-block kb uses kb % n_main); one more for the cross terms
   int tmem_cols;      // power of two >= max(32, (n_main + 1) * n_pad)
+  // Fused head: the NEXT (last) layer of the hasher, out_dim = head_n <= 16 (nlsh/hashings.py:19-22 output_layer),
+  // computed by the epilogue on the CUDA cores from this layer's activations while they are in registers:
+  // logits[row, j] = head_b[j] + sum_c act(...)[row, c] * head_w[j, c] (fp32 FMA chain in ascending c).  As a
+  // tcgen05 layer it is 96 MMAs of N = 16 - the issue cost of a 256-wide layer for 1/16 of its work - plus a
+  // launch and a round trip of the split activations.
+  const float* head_w;  // [head_n, N] fp32 or nullptr
+  const float* head_b;  // [head_n] or nullptr
+  int head_n;
 };
+
+constexpr int kHeadMax = 16;
 
 __global__ void __launch_bounds__(kTcThreads, 1)
     tc_linear_kernel(const TcArgs a, const __grid_constant__ CUtensorMap map_a_hi,
@@ -59,6 +69,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   uint64_t* empty_bar = full_bar + 4;                      // [stages <= 4]
   uint64_t* acc_bar = empty_bar + 4;                       // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  float* head_s = reinterpret_cast<float*>(tail + 256);  // [n_pad][kHeadMax] head weights, column-major groups
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -136,6 +147,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     __syncwarp();
   } else {
     // ------------------------------- epilogue (warps 0-3) -------------------------------
+    const bool fused = a.head_w != nullptr;
+    if (fused) {  // stage the head weights while the MMAs run: head_s[c][j] = head_w[j][c], zero padded
+      for (int idx = tid; idx < a.n_pad * kHeadMax; idx += 128) {
+        const int c = idx / kHeadMax, j = idx % kHeadMax;
+        head_s[idx] = (j < a.head_n && c < a.N) ? a.head_w[(size_t)j * a.N + c] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+    }
+    float logit[kHeadMax];
+#pragma unroll
+    for (int j = 0; j < kHeadMax; ++j) logit[j] = 0.f;
     mbar_wait_poll(acc_bar, 0);
     tc_fence_after();
     const int row = m0 + warp * 32 + lane;  // TMEM lane = accumulator row
@@ -162,6 +184,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int col = c0 + i;
         float x = v[i] + ((a.bias != nullptr && col < a.N) ? a.bias[col] : 0.f);
         v[i] = tc_act(x, a.act, a.act_scale);
+      }
+      if (fused) {  // 16 columns x 16 head outputs (columns / outputs past the layer hold zero weights)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4* w = reinterpret_cast<const float4*>(head_s + (size_t)(c0 + i) * kHeadMax);
+#pragma unroll
+          for (int j4 = 0; j4 < kHeadMax / 4; ++j4) {
+            const float4 ww = w[j4];  // the same address in every lane: a broadcast
+            logit[4 * j4 + 0] = fmaf(v[i], ww.x, logit[4 * j4 + 0]);
+            logit[4 * j4 + 1] = fmaf(v[i], ww.y, logit[4 * j4 + 1]);
+            logit[4 * j4 + 2] = fmaf(v[i], ww.z, logit[4 * j4 + 2]);
+            logit[4 * j4 + 3] = fmaf(v[i], ww.w, logit[4 * j4 + 3]);
+          }
+        }
+        continue;
       }
       if (!row_ok) continue;
       if (!last) {
@@ -200,7 +237,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
       }
     }
-    if (last && row_ok && a.codes_out) a.codes_out[row] = code;
+    if (fused && row_ok) {
+#pragma unroll
+      for (int j = 0; j < kHeadMax; ++j) {
+        if (j < a.head_n) {
+          const float l = logit[j] + (a.head_b != nullptr ? a.head_b[j] : 0.f);
+          if (a.out_full) a.out_full[(size_t)row * a.ld_out + j] = l;
+          if (a.head == NLSH_HEAD_SOFTMAX) {
+            if (j == 0 || l > best) {
+              best = l;
+              code = j;
+            }
+          } else {
+            code = (code << 1) | (l > thr ? 1 : 0);  // MSB first (utils.pyx:12-14)
+          }
+        }
+      }
+    }
+    if ((last || fused) && row_ok && a.codes_out) a.codes_out[row] = code;
   }
 
   tc_fence_before();
@@ -277,8 +331,15 @@ int nlsh_tc_split(const float* x, size_t n, float* hi, float* lo, cudaStream_t s
 int nlsh_tc_linear(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo,
                    const float* bias, int M, int N, int K, int act, float act_scale, float* out_hi,
                    float* out_lo, float* out_full, int ld_out, int* codes_out, int head,
-                   cudaStream_t st) {
+                   cudaStream_t st, const float* head_w, const float* head_b, int head_n) {
   TcArgs a{};
+  a.head_w = head_w;
+  a.head_b = head_b;
+  a.head_n = head_w != nullptr ? head_n : 0;
+  if (head_w != nullptr && (head_n < 1 || head_n > kHeadMax)) {
+    nlsh_set_error("tc_linear: fused head of %d outputs (1..%d)", head_n, kHeadMax);
+    return NLSH_ERR_INVALID;
+  }
   a.bias = bias;
   a.out_hi = out_hi;
   a.out_lo = out_lo;
@@ -299,9 +360,10 @@ int nlsh_tc_linear(const float* a_hi, const float* a_lo, const float* w_hi, cons
   while (a.tmem_cols < (a.n_main + 1) * a.n_pad) a.tmem_cols *= 2;
   const size_t stage_bytes =
       2 * (size_t)kTcBM * kTcBK * sizeof(float) + 2 * (size_t)a.n_pad * kTcBK * sizeof(float);
+  const size_t head_bytes = head_w != nullptr ? (size_t)a.n_pad * kHeadMax * sizeof(float) : 0;
   a.stages = 4;
-  while (a.stages > 1 && a.stages * stage_bytes + 2048 > 220 * 1024) --a.stages;
-  const size_t smem = a.stages * stage_bytes + 2048;
+  while (a.stages > 1 && a.stages * stage_bytes + 2048 + head_bytes > 220 * 1024) --a.stages;
+  const size_t smem = a.stages * stage_bytes + 2048 + head_bytes;
 
   CUtensorMap m_a_hi, m_a_lo, m_w_hi, m_w_lo;
   int rc;
