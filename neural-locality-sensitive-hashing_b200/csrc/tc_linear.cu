@@ -54,6 +54,7 @@ struct TcArgs {
 
 constexpr int kHeadMax = 16;
 
+template <bool FUSED>  // FUSED: the hasher's output layer rides in this layer's epilogue (TcArgs::head_w)
 __global__ void __launch_bounds__(kTcThreads, 1)
     tc_linear_kernel(const TcArgs a, const __grid_constant__ CUtensorMap map_a_hi,
                      const __grid_constant__ CUtensorMap map_a_lo,
@@ -147,17 +148,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     __syncwarp();
   } else {
     // ------------------------------- epilogue (warps 0-3) -------------------------------
-    const bool fused = a.head_w != nullptr;
+    constexpr bool fused = FUSED;
     if (fused) {  // stage the head weights while the MMAs run: head_s[c][j] = head_w[j][c], zero padded
-      for (int idx = tid; idx < a.n_pad * kHeadMax; idx += 128) {
-        const int c = idx / kHeadMax, j = idx % kHeadMax;
-        head_s[idx] = (j < a.head_n && c < a.N) ? a.head_w[(size_t)j * a.N + c] : 0.f;
+#pragma unroll 4
+      for (int idx = tid; idx < a.n_pad * kHeadMax; idx += 128) {  // coalesced reads along c
+        const int j = idx / a.n_pad, c = idx - j * a.n_pad;
+        head_s[c * kHeadMax + j] = (j < a.head_n && c < a.N) ? a.head_w[(size_t)j * a.N + c] : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
     }
-    float logit[kHeadMax];
+    float logit[FUSED ? kHeadMax : 1];
 #pragma unroll
-    for (int j = 0; j < kHeadMax; ++j) logit[j] = 0.f;
+    for (int j = 0; j < (FUSED ? kHeadMax : 1); ++j) logit[j] = 0.f;
     mbar_wait_poll(acc_bar, 0);
     tc_fence_after();
     const int row = m0 + warp * 32 + lane;  // TMEM lane = accumulator row
@@ -170,22 +172,34 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int n_main_used = a.n_main < n_kblocks ? a.n_main : n_kblocks;
     for (int c0 = 0; c0 < a.n_pad; c0 += 16) {
       float v[16], t[16];
-      tc_ld16(lane_addr + (uint32_t)c0, v);  // warp-collective: every lane takes part
+      {  // first hi*hi accumulator and the cross-term accumulator in flight together (warp-collective loads)
+        uint32_t vr[16], tr[16];
+        tc_ld16_nowait(lane_addr + (uint32_t)c0, vr);
+        tc_ld16_nowait(lane_addr + (uint32_t)(a.n_main * a.n_pad + c0), tr);
+        tc_wait_ld2(vr, tr);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] = __uint_as_float(vr[i]);
+          t[i] = __uint_as_float(tr[i]);
+        }
+      }
+      float cross[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cross[i] = t[i];
       for (int j = 1; j < n_main_used; ++j) {
         tc_ld16(lane_addr + (uint32_t)(j * a.n_pad + c0), t);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += t[i];
       }
-      tc_ld16(lane_addr + (uint32_t)(a.n_main * a.n_pad + c0), t);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += t[i];
+      for (int i = 0; i < 16; ++i) v[i] += cross[i];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int col = c0 + i;
         float x = v[i] + ((a.bias != nullptr && col < a.N) ? a.bias[col] : 0.f);
         v[i] = tc_act(x, a.act, a.act_scale);
       }
-      if (fused) {  // 16 columns x 16 head outputs (columns / outputs past the layer hold zero weights)
+      if constexpr (FUSED) {  // 16 columns x 16 head outputs (columns / outputs past the layer hold zero weights)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float4* w = reinterpret_cast<const float4*>(head_s + (size_t)(c0 + i) * kHeadMax);
@@ -237,7 +251,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
       }
     }
-    if (fused && row_ok) {
+    if constexpr (FUSED) {
+      if (row_ok) {
 #pragma unroll
       for (int j = 0; j < kHeadMax; ++j) {
         if (j < a.head_n) {
@@ -252,6 +267,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             code = (code << 1) | (l > thr ? 1 : 0);  // MSB first (utils.pyx:12-14)
           }
         }
+      }
       }
     }
     if ((last || fused) && row_ok && a.codes_out) a.codes_out[row] = code;
@@ -371,9 +387,9 @@ int nlsh_tc_linear(const float* a_hi, const float* a_lo, const float* w_hi, cons
   if ((rc = tc_make_map(&m_a_lo, a_lo, M, K, kTcBM)) != NLSH_OK) return rc;
   if ((rc = tc_make_map(&m_w_hi, w_hi, N, K, a.n_pad)) != NLSH_OK) return rc;
   if ((rc = tc_make_map(&m_w_lo, w_lo, N, K, a.n_pad)) != NLSH_OK) return rc;
-  NLSH_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
+  auto kern = head_w != nullptr ? tc_linear_kernel<true> : tc_linear_kernel<false>;
+  NLSH_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)((M + kTcBM - 1) / kTcBM);
-  tc_linear_kernel<<<grid, kTcThreads, smem, st>>>(a, m_a_hi, m_a_lo, m_w_hi, m_w_lo);
+  kern<<<grid, kTcThreads, smem, st>>>(a, m_a_hi, m_a_lo, m_w_hi, m_w_lo);
   return nlsh_check_cuda(nlsh_post_launch(), "tc_linear_kernel launch");
 }
