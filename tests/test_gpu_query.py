@@ -159,11 +159,16 @@ def test_tensor_core_filter_is_exact(monkeypatch, n, d, hs, nq, p, k, metric, ki
     assert (ids[:, 0] >= 0).all()
     # the same through the filter's other regimes: candidate buffers of k entries (almost every query
     # overflows and is re-scanned exactly in the merge), no threshold ladder (seed bound only), no seed
-    # (bound +inf: every row is scored), the scorer's query from global / shared memory, 16 SMs left free,
-    # 128 / 32 queries per item
+    # (bound +inf: every row is scored), the scorer's query from global / shared memory (the latter with the
+    # lazy item release), 16 SMs left free, 128 / 32 queries per item
     for flags, env in ((4, {}), (0, {"NLSH_TC_LADDER": "0"}), (0, {"NLSH_SCAN_SEED": "0"}),
                        (0, {"NLSH_TC_QGLOBAL": "1"}), (0, {"NLSH_TC_QGLOBAL": "0"}), (16 << 8, {}),
-                       (0, {"NLSH_TC_NQ": "128"}), (0, {"NLSH_TC_NQ": "32"})):
+                       (0, {"NLSH_TC_NQ": "128"}), (0, {"NLSH_TC_NQ": "32"}),
+                       # 32-byte row loads on / off with either query source, the accumulator ring 2 / 16 deep,
+                       # the shallowest slot ring
+                       (0, {"NLSH_TC_V8": "1", "NLSH_TC_QGLOBAL": "1"}), (0, {"NLSH_TC_V8": "1", "NLSH_TC_QGLOBAL": "0"}),
+                       (0, {"NLSH_TC_V8": "0", "NLSH_TC_QGLOBAL": "0"}), (0, {"NLSH_TC_SETS": "2"}),
+                       (0, {"NLSH_TC_SETS": "16"}), (0, {"NLSH_TC_SLOTS": "3"})):
         if env.get("NLSH_SCAN_SEED") == "0" and n * nq * p > 2e9:
             continue  # scoring every pair one thread at a time is only for the small cases
         for name, val in env.items():

@@ -46,3 +46,14 @@ def test_tc_path_matches_fp64_and_simt(m, dims):
     # codes are exactly the threshold rule applied to the path's own logits
     from nlsh import _native
     assert torch.equal(_native.codes_from_logits(tc_logits, 0), tc_codes)
+    # the default fuses the output layer into the epilogue of the layer before it (tc_linear.cu, TcArgs::head_w);
+    # as a tcgen05 layer of its own it must meet the same bar
+    os.environ["NLSH_MLP_FUSE_HEAD"] = "0"
+    try:
+        un_logits, un_codes = run_mlp(xs, wsc, bsc)
+    finally:
+        os.environ.pop("NLSH_MLP_FUSE_HEAD")
+    err_un = ((un_logits.cpu().double() - ref).abs() / scale).max().item()
+    assert err_un < 1e-5, err_un
+    assert torch.equal(_native.codes_from_logits(un_logits, 0), un_codes)
+    assert (un_codes == tc_codes).float().mean().item() >= 0.999
