@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NLSH_B200_VERSION 310 /* 0.3.0: scan flags bit 2; tensor-core scan with per-query candidate buffers */
+#define NLSH_B200_VERSION 310 /* 0.3.1: + nlsh_sample_probes, nlsh_query_seed_tau_rows; scan pipeline with a tile streamer */
 
 #define NLSH_OK 0
 #define NLSH_ERR_INVALID (-1)   /* bad argument (-> ValueError in the Python layer) */
