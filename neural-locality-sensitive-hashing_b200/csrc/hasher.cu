@@ -378,7 +378,15 @@ TcPlan tc_plan(int64_t n, const nlsh_layer_t* layers, int32_t n_layers) {
     if (layers[l].in_dim > width) width = layers[l].in_dim;
     p.weight_floats += (size_t)layers[l].in_dim * layers[l].out_dim;
   }
-  int64_t chunk = width > 512 ? 16384 : kMlpChunkRows;
+  // Rows per chunk of the tensor-core path: whole waves of 128-row CTAs - two per SM-count (37 888 rows on 148 SMs:
+  // a 32 768-row chunk is 1.73 waves and pays for two) - while a chunk's split activations stay about L2 sized;
+  // one wave for very wide inputs.  NLSH_MLP_CHUNK=<rows> overrides (A/B runs).
+  const int64_t wave = (int64_t)nlsh_num_sms() * 128;
+  int64_t chunk = width > 512 ? wave : 2 * wave;
+  if (const char* env = getenv("NLSH_MLP_CHUNK")) {
+    const long long v = atoll(env);
+    if (v >= 128) chunk = v;
+  }
   if (n < chunk) chunk = n > 0 ? n : 1;
   p.chunk = chunk;
   p.act_floats = (size_t)chunk * width;
