@@ -44,6 +44,15 @@ def test_argument_validation_without_gpu():
                                   None, None, None, 0, 0, None) == _native.ERR_INVALID
     assert "metric" in _native.last_error()
     assert L.nlsh_build_csr(None, -1, 4, None, 0, None, None, None, None, None, 0, None) == _native.ERR_INVALID
+    # sampled multi-probe: only the bit hashers sample (hashings.py:66-92), p and hash_size bounded
+    assert L.nlsh_sample_probes(None, 4, 12, _native.HEAD_SOFTMAX, 4, 1, None, None) == _native.ERR_INVALID
+    assert "Bernoulli" in _native.last_error()
+    assert L.nlsh_sample_probes(None, 4, 12, _native.HEAD_SIGMOID, 0, 1, None, None) == _native.ERR_INVALID
+    assert L.nlsh_sample_probes(None, 4, 12, _native.HEAD_SIGMOID, 4, 1, None, None) == _native.ERR_INVALID  # NULLs
+    assert L.nlsh_sample_probes(None, 0, 12, _native.HEAD_SIGMOID, 4, 1, None, None) == _native.OK  # empty batch
+    # seed with a caller-chosen sample: the sample size is bounded
+    assert L.nlsh_query_seed_tau_rows(None, 1, 8, None, 1, None, 4, None, 0, 0, 10, -1, None, None, 0,
+                                      None) == _native.ERR_INVALID
     assert L.nlsh_build_workspace_bytes(1000, 16) > 0
     assert L.nlsh_query_workspace_bytes(100, 4, 10, 128, 256, 10000, 100) > 0
     assert L.nlsh_knn_workspace_bytes(100, 1000, 128, 10) > 0
